@@ -1,0 +1,269 @@
+/*
+ * magical_b200.h — C ABI of the B200-native MAGICAL hot path.
+ *
+ * The reference (qxcv/magical) has no FFI of its own: its hot path is
+ * `BaseEnv.step()` (magical/base_env.py:255-292), which hands the physics to
+ * pymunk/Chipmunk2D (`pm.Space.step`, base_env.py:236-243), the two-camera
+ * render to pyglet/OpenGL (base_env.py:309-338, gym_render.py:208-249) and the
+ * 96x96 downsample + frame stack to OpenCV/gym wrappers
+ * (benchmarks/__init__.py:46-274).  This header is the boundary that replaces
+ * those three native call sites with ONE batched library: plain pointers and
+ * sizes, no torch types, loadable with ctypes (see INTEGRATION.md for the
+ * reference-side binding).
+ *
+ * Data model
+ *   - A *compiled scene* (`mg_scene_t`) is the flat-table form of what
+ *     `Entity.setup()` builds imperatively in the reference
+ *     (entities.py:238-437, 502-537, 614-757, 790-819): bodies, collision
+ *     shapes, joints, draw primitives, goal sensors and score metadata.  The
+ *     Python host code (magical_b200/entities.py) produces it.
+ *   - A handle owns `n_scenes` compiled scenes and `batch` environments, each
+ *     bound to one scene index; all simulator state lives in device memory.
+ *   - The observation buffer is caller-owned device memory (e.g. a torch uint8
+ *     tensor's data_ptr) that stays bound to the handle: the frame stack is
+ *     shifted in place inside it every step.
+ *
+ * Error model: every entry point returns 0 on success or a negative MG_E_*
+ * code; `mg_last_error()` returns a thread-local message.  Nothing throws
+ * across the ABI.  A handle must be used from one host thread at a time.
+ * Kernels are enqueued on the stream given at `mg_create`; `mg_step` does not
+ * synchronise.
+ */
+#ifndef MAGICAL_B200_H
+#define MAGICAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_ABI_VERSION 1
+
+/* capacity limits of one compiled scene */
+#define MG_MAX_BODIES 16   /* non-static bodies (<=15 dynamic + 1 kinematic) */
+#define MG_MAX_SHAPES 72   /* solid collision shapes incl. the 4 arena walls */
+#define MG_MAX_CVERTS 384  /* collision vertex pool (double2) */
+#define MG_MAX_JOINTS 32
+#define MG_MAX_CGROUPS 20  /* collision groups: one per shaped body + 4 walls */
+#define MG_MAX_BPAIRS 160  /* candidate collision-group pairs */
+#define MG_MAX_GOALS 3
+#define MG_MAX_BLOCKS 10
+#define MG_MAX_PRIMS 160   /* draw primitives */
+#define MG_MAX_DVERTS 704  /* draw vertex pool (float2) */
+
+/* error codes */
+#define MG_OK 0
+#define MG_E_INVALID -1   /* bad argument */
+#define MG_E_CUDA -2      /* CUDA runtime failure (message has the detail) */
+#define MG_E_NOMEM -3
+#define MG_E_STATE -4     /* call not valid in the handle's current state */
+
+/* shape kinds (Chipmunk's type order: circle < segment < poly) */
+enum { MG_SHAPE_CIRCLE = 0, MG_SHAPE_SEGMENT = 1, MG_SHAPE_POLY = 2 };
+/* body kinds */
+enum { MG_BODY_DYNAMIC = 0, MG_BODY_KINEMATIC = 1 };
+/* joint kinds, the six pymunk constraints the reference uses
+ * (entities.py:255-277, 334-354, 703-711) */
+enum {
+  MG_JOINT_PIVOT = 0,
+  MG_JOINT_GEAR = 1,
+  MG_JOINT_ROTARY_SPRING = 2,
+  MG_JOINT_PIN = 3,
+  MG_JOINT_ROTARY_LIMIT = 4,
+  MG_JOINT_MOTOR = 5
+};
+/* draw primitive kinds / transforms */
+enum { MG_PRIM_POLY = 0, MG_PRIM_NGON = 1, MG_PRIM_LINELOOP = 2 };
+enum { MG_XFORM_WORLD = 0, MG_XFORM_BODY = 1, MG_XFORM_PUPIL = 2 };
+/* tasks (score function selector), benchmarks/<task>.py */
+enum {
+  MG_TASK_MOVE_TO_CORNER = 0,
+  MG_TASK_MOVE_TO_REGION = 1,
+  MG_TASK_MATCH_REGIONS = 2,
+  MG_TASK_MAKE_LINE = 3,
+  MG_TASK_FIND_DUPE = 4,
+  MG_TASK_FIX_COLOUR = 5,
+  MG_TASK_CLUSTER_COLOUR = 6,
+  MG_TASK_CLUSTER_SHAPE = 7
+};
+/* observation layouts = the reference's preprocessors
+ * (benchmarks/__init__.py:242-274) plus the raw two-view dict */
+enum {
+  MG_OBS_LORES4E = 0,    /* u8 [B,96,96,12]  4 ego frames, oldest first     */
+  MG_OBS_LORES4A = 1,    /* u8 [B,96,96,12]  4 allo frames                  */
+  MG_OBS_LORES3EA = 2,   /* u8 [B,96,96,12]  1 allo + 3 ego                 */
+  MG_OBS_LORESSTACK = 3, /* u8 [2,B,96,96,12] plane 0 = allo, plane 1 = ego */
+  MG_OBS_LORESCHW4E = 4, /* u8 [B,12,96,96]                                 */
+  MG_OBS_RAW = 5         /* u8 [2,B,res,res,3] plane 0 = allo, 1 = ego      */
+};
+
+typedef struct {
+  double m_inv, i_inv; /* 0 for kinematic bodies */
+  double p0[2];        /* pose at reset */
+  double a0;
+  int32_t kind;
+  int32_t pad_;
+} mg_body_t;
+
+typedef struct {
+  int32_t kind;   /* MG_SHAPE_* */
+  int32_t body;   /* -1 = the static body */
+  int32_t vert0;  /* first vertex in cverts: circle 1 (centre), segment 2, poly n */
+  int32_t nvert;
+  double radius;  /* circle radius / segment radius / poly bevel radius */
+  double friction;
+  int32_t group;  /* Chipmunk ShapeFilter group, 0 = none */
+  int32_t pad_;
+} mg_shape_t;
+
+typedef struct {
+  int32_t kind; /* MG_JOINT_* */
+  int32_t a, b; /* body indices, -1 = static body */
+  int32_t pad_;
+  double anchor_a[2], anchor_b[2];
+  /* gear: p0=phase p1=ratio | spring: p0=rest p1=stiffness p2=damping |
+   * limit: p0=min p1=max | pin: p0=rest distance */
+  double p0, p1, p2;
+  double max_force, max_bias, error_bias;
+} mg_joint_t;
+
+typedef struct {
+  uint8_t shape0, nshape; /* contiguous shape range */
+  int8_t body;            /* -1 static */
+  uint8_t robot_group;    /* 1 if the shapes carry the robot's filter group */
+} mg_cgroup_t;
+
+typedef struct {
+  uint8_t kind;   /* MG_PRIM_* */
+  uint8_t xform;  /* MG_XFORM_* */
+  uint8_t body;   /* body whose pose places the primitive (XFORM_BODY/PUPIL) */
+  uint8_t body2;  /* XFORM_PUPIL: the eye body whose angle spins the pupil */
+  uint8_t rgb[3];
+  uint8_t nvert;  /* POLY/LINELOOP: vertex count; NGON: number of sides */
+  uint16_t vert0; /* POLY/LINELOOP: first vertex in dverts */
+  uint16_t stipple; /* LINELOOP: 16-bit GL stipple pattern, 0xFFFF = solid */
+  float cx, cy;   /* NGON: centre in the body frame (eye offset for pupils) */
+  float radius;   /* NGON: circumradius; LINELOOP: width in 384-res pixels */
+  float ex, ey;   /* PUPIL: offset applied before the pupil's own rotation */
+} mg_prim_t;
+
+typedef struct {
+  double cx, cy, w, h; /* sensor box centre and size (entities.py:794-797) */
+  int32_t colour;
+  int32_t expect_block; /* FixColour: block that must be the only one inside, -1 = must be empty */
+} mg_goal_t;
+
+typedef struct {
+  int32_t body;       /* body index */
+  int32_t cgroup;     /* collision group holding all its shapes */
+  int32_t shape_type; /* 0 square 1 pentagon 2 star 3 circle 4 triangle 5 hexagon 6 octagon */
+  int32_t colour;     /* 0 red 1 green 2 blue 3 yellow */
+  int32_t role;       /* task-specific: 1 target, 2 distractor, 0 none */
+  int32_t label;      /* Cluster*: index of the block's cluster value */
+} mg_block_t;
+
+typedef struct {
+  /* ---- header ---- */
+  int32_t task;           /* MG_TASK_* */
+  int32_t max_steps;      /* episode length (benchmarks/__init__.py:407-813) */
+  int32_t debug_reward;   /* MoveToCorner DebugReward variant */
+  int32_t n_bodies, n_shapes, n_cverts, n_joints, n_cgroups, n_bpairs;
+  int32_t n_goals, n_blocks, n_prims, n_dverts;
+  int32_t n_labels;       /* Cluster*: number of distinct cluster values */
+  /* robot wiring for Robot.update (entities.py:459-479) */
+  int32_t robot_body, control_body;
+  int32_t finger_body[2], motor_joint[2], eye_body[2];
+  int32_t pad_[2];
+  double robot_radius;
+  /* ---- tables ---- */
+  mg_body_t bodies[MG_MAX_BODIES];
+  mg_shape_t shapes[MG_MAX_SHAPES];
+  double cverts[MG_MAX_CVERTS][2];
+  mg_joint_t joints[MG_MAX_JOINTS];
+  mg_cgroup_t cgroups[MG_MAX_CGROUPS];
+  uint8_t bpairs[MG_MAX_BPAIRS][2]; /* canonical arbiter order */
+  mg_goal_t goals[MG_MAX_GOALS];
+  mg_block_t blocks[MG_MAX_BLOCKS];
+  mg_prim_t prims[MG_MAX_PRIMS];   /* painter's order */
+  float dverts[MG_MAX_DVERTS][2];
+} mg_scene_t;
+
+typedef struct {
+  int32_t device;       /* CUDA device ordinal */
+  int32_t batch;        /* environments owned by this handle */
+  int32_t n_scenes;
+  int32_t obs_mode;     /* MG_OBS_* */
+  int32_t res;          /* MG_OBS_RAW: render resolution (384); ignored otherwise */
+  int32_t auto_reset;   /* 1: envs that finish an episode are reset inside mg_step
+                              and the returned observation is the new episode's first */
+  int32_t fast_math;    /* 0: fp64, contraction off (parity build); 1: fp64 with FMA */
+  int32_t reserved_[9];
+} mg_config_t;
+
+/* One environment's simulator state in host-readable form (parity tests). */
+typedef struct {
+  int32_t n_bodies, n_joints, n_contacts, episode_steps;
+  int32_t scene, overflow, pad_[2];
+  double pos[MG_MAX_BODIES][2];
+  double angle[MG_MAX_BODIES];
+  double vel[MG_MAX_BODIES][2];
+  double angvel[MG_MAX_BODIES];
+  double joint_acc[MG_MAX_JOINTS][2]; /* accumulated impulses (jAcc / jnAcc) */
+  int32_t contact_shapes[32][2];
+  double contact_jn[32], contact_jt[32];
+} mg_state_t;
+
+typedef struct mg_handle mg_handle;
+
+int mg_version(void);
+const char* mg_last_error(void);
+/* sizeof(mg_scene_t) / sizeof(mg_state_t) as compiled, so a binding can check its struct layout. */
+int64_t mg_sizeof_scene(void);
+int64_t mg_sizeof_state(void);
+
+/* Create `cfg->batch` environments on `cfg->device`.  `scenes` is a host array of
+ * cfg->n_scenes compiled scenes (copied).  `cuda_stream` is a cudaStream_t (NULL = legacy
+ * default stream).  Replaces BaseEnv.__init__ + Viewer creation (base_env.py:78-122,184-190). */
+int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_stream, mg_handle** out);
+int mg_destroy(mg_handle* h);
+
+/* Bind the caller-owned DEVICE observation buffer (layout per cfg->obs_mode). */
+int mg_bind_obs(mg_handle* h, void* obs_dev, int64_t nbytes);
+int64_t mg_obs_nbytes(const mg_handle* h);
+
+/* Reset environments: BaseEnv.reset (base_env.py:177-234) + FlattenFrameStack.reset
+ * (benchmarks/__init__.py:130-136).  env_ids: HOST int32[n] (NULL => all); scene_ids: HOST
+ * int32[n] scene index per reset env (NULL => keep each env's current scene, initially 0).
+ * Renders the first observation into the bound buffer (frame replicated over the stack). */
+int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* scene_ids);
+
+/* One env-step for the whole batch: Robot.set_action + 10 x (Robot.update + Space.step)
+ * + episode bookkeeping + score + render + stack (base_env.py:255-292).
+ * actions: DEVICE int32[batch] in [0,18).  reward/done/score: DEVICE, caller-owned, [batch]
+ * (any may be NULL).  The observation lands in the bound buffer. */
+int mg_step(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev,
+            float* score_dev);
+
+/* Physics only (no render): used by parity tests and the physics-only bench leg. */
+int mg_step_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev,
+                    uint8_t* done_dev, float* score_dev);
+/* Render + stack only, from the current state. */
+int mg_render(mg_handle* h);
+
+/* Evaluate each env's end-of-trajectory score for its CURRENT state
+ * (score_on_end_of_traj of the env's task); score_dev: DEVICE float[batch]. */
+int mg_score(mg_handle* h, float* score_dev);
+
+/* Host-readable snapshot / overwrite of one environment (synchronises the stream). */
+int mg_get_state(mg_handle* h, int32_t env, mg_state_t* out);
+int mg_set_pose(mg_handle* h, int32_t env, int32_t body, double x, double y, double angle);
+
+/* Number of kernels launched by this handle since creation (bench bookkeeping). */
+int64_t mg_launch_count(const mg_handle* h);
+int mg_synchronize(mg_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGICAL_B200_H */
