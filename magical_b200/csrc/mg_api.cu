@@ -1,0 +1,319 @@
+/*
+ * mg_api.cu — the C ABI declared in include/magical_b200.h (host side).
+ *
+ * One handle = one batch of environments on one GPU.  It owns the compiled
+ * scenes (+ derived constants) and the per-environment state records in HBM,
+ * and enqueues three kernels per env-step on the caller's stream:
+ *   K1 k_physics  (mg_physics.cu)  10 sub-steps of rigid-body physics
+ *   K2 k_finish   (mg_finish.cu)   step counter, done, score, reward, auto-reset
+ *   K3 k_raster   (mg_raster.cu)   render + downsample + frame stack into the bound obs buffer
+ * Reference call sites replaced: base_env.py:177-338 (reset/step/render).
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "mg_device.cuh"
+#include "mg_sincos.h"
+
+cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
+                              cudaStream_t stream);
+cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int batch, int auto_reset, int mode,
+                             float* reward, uint8_t* done, float* score, cudaStream_t stream);
+cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
+                            const int32_t* scene_ids, int first_time, cudaStream_t stream);
+cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
+                             int res_out, int ecap, int only_fresh, cudaStream_t stream);
+cudaError_t mg_raster_upload_units(const double* units);
+size_t mg_raster_smem_bytes(int mode, int ecap);
+
+struct mg_handle {
+  mg_config_t cfg;
+  cudaStream_t stream;
+  EnvState* d_states;
+  DeviceScene* d_scenes;
+  int32_t* d_ids;       /* scratch for mg_reset */
+  int32_t* d_scene_ids;
+  uint8_t* obs;
+  int64_t obs_bytes;
+  int res_out;
+  int ecap;
+  int64_t launches;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* detail) {
+  snprintf(g_err, sizeof(g_err), fmt, detail ? detail : "");
+  return code;
+}
+#define CUDA_TRY(expr)                                                      \
+  do {                                                                      \
+    cudaError_t e_ = (expr);                                                \
+    if (e_ != cudaSuccess) return fail(MG_E_CUDA, #expr ": %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" {
+
+int mg_version(void) { return MG_ABI_VERSION; }
+const char* mg_last_error(void) { return g_err; }
+int64_t mg_sizeof_scene(void) { return (int64_t)sizeof(mg_scene_t); }
+int64_t mg_sizeof_state(void) { return (int64_t)sizeof(mg_state_t); }
+
+static int64_t obs_bytes_for(const mg_config_t* cfg, int res_out) {
+  int64_t px = (int64_t)res_out * res_out;
+  switch (cfg->obs_mode) {
+    case MG_OBS_LORES4E:
+    case MG_OBS_LORES4A:
+    case MG_OBS_LORES3EA:
+    case MG_OBS_LORESCHW4E:
+      return (int64_t)cfg->batch * px * 12;
+    case MG_OBS_LORESSTACK:
+      return 2 * (int64_t)cfg->batch * px * 12;
+    case MG_OBS_RAW:
+      return 2 * (int64_t)cfg->batch * px * 3;
+  }
+  return -1;
+}
+
+int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_stream, mg_handle** out) {
+  if (!cfg || !scenes || !out) return fail(MG_E_INVALID, "mg_create: null argument%s", "");
+  if (cfg->batch <= 0 || cfg->n_scenes <= 0) return fail(MG_E_INVALID, "mg_create: batch and n_scenes must be > 0%s", "");
+  if (cfg->obs_mode < MG_OBS_LORES4E || cfg->obs_mode > MG_OBS_RAW) return fail(MG_E_INVALID, "mg_create: bad obs_mode%s", "");
+  int res_out = 96;
+  if (cfg->obs_mode == MG_OBS_RAW) {
+    res_out = cfg->res > 0 ? cfg->res : 384;
+    if (res_out % 48 != 0) return fail(MG_E_INVALID, "mg_create: raw resolution must be a multiple of 48%s", "");
+  }
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(MG_E_INVALID, "mg_create: no such CUDA device%s", "");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+
+  /* derive per-scene constants on the host */
+  std::vector<DeviceScene> host(cfg->n_scenes);
+  int ecap = 64;
+  for (int i = 0; i < cfg->n_scenes; i++) {
+    host[i].s = scenes[i];
+    const char* why = mg_build_scene_aux(&scenes[i], &host[i].aux);
+    if (why) return fail(MG_E_INVALID, "mg_create: scene rejected: %s", why);
+    int edges = 0, rprims = 0;
+    for (int p = 0; p < scenes[i].n_prims; p++) {
+      const mg_prim_t& pr = scenes[i].prims[p];
+      edges += pr.nvert;
+      rprims += pr.kind == MG_PRIM_LINELOOP ? pr.nvert : 1;
+      if (pr.kind == MG_PRIM_NGON && pr.nvert != 10 && pr.nvert != 20 && pr.nvert != 100)
+        return fail(MG_E_INVALID, "mg_create: NGON primitives must have 10, 20 or 100 sides%s", "");
+      if (pr.kind != MG_PRIM_NGON && (int)pr.vert0 + pr.nvert > MG_MAX_DVERTS)
+        return fail(MG_E_INVALID, "mg_create: draw vertex range%s", "");
+    }
+    if (rprims > 192) return fail(MG_E_INVALID, "mg_create: too many draw primitives in one scene%s", "");
+    if (edges > ecap) ecap = edges;
+  }
+  ecap = (ecap + 63) / 64 * 64;
+  if (mg_raster_smem_bytes(cfg->obs_mode, ecap) > 200 * 1024)
+    return fail(MG_E_INVALID, "mg_create: scene has too many draw edges for the rasteriser's shared memory%s", "");
+
+  mg_handle* h = new (std::nothrow) mg_handle();
+  if (!h) return fail(MG_E_NOMEM, "mg_create: out of host memory%s", "");
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->stream = (cudaStream_t)cuda_stream;
+  h->res_out = res_out;
+  h->ecap = ecap;
+  h->obs_bytes = obs_bytes_for(cfg, res_out);
+  cudaError_t e;
+  if ((e = cudaMalloc(&h->d_states, sizeof(EnvState) * (size_t)cfg->batch)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_scenes, sizeof(DeviceScene) * (size_t)cfg->n_scenes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_scene_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess) {
+    mg_destroy(h);
+    return fail(MG_E_NOMEM, "mg_create: cudaMalloc: %s", cudaGetErrorString(e));
+  }
+  if ((e = cudaMemcpyAsync(h->d_scenes, host.data(), sizeof(DeviceScene) * (size_t)cfg->n_scenes, cudaMemcpyHostToDevice,
+                           h->stream)) != cudaSuccess ||
+      (e = cudaMemsetAsync(h->d_states, 0, sizeof(EnvState) * (size_t)cfg->batch, h->stream)) != cudaSuccess) {
+    mg_destroy(h);
+    return fail(MG_E_CUDA, "mg_create: upload: %s", cudaGetErrorString(e));
+  }
+  /* unit circles for 10/20/100-gons: gym_render.make_circle (gym_render.py:438-446) */
+  double units[130][2];
+  const int ns[3] = {10, 20, 100}, offs[3] = {0, 10, 30};
+  for (int t = 0; t < 3; t++)
+    for (int k = 0; k < ns[t]; k++) {
+      double ang = 2 * M_PI * k / ns[t];
+      units[offs[t] + k][0] = cos(ang);
+      units[offs[t] + k][1] = sin(ang);
+    }
+  if ((e = mg_raster_upload_units(&units[0][0])) != cudaSuccess ||
+      (e = mg_launch_reset(h->d_states, h->d_scenes, cfg->batch, nullptr, nullptr, 1, h->stream)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(h->stream)) != cudaSuccess) {
+    mg_destroy(h);
+    return fail(MG_E_CUDA, "mg_create: init: %s", cudaGetErrorString(e));
+  }
+  h->launches = 1;
+  *out = h;
+  return MG_OK;
+}
+
+int mg_destroy(mg_handle* h) {
+  if (!h) return MG_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_states);
+  cudaFree(h->d_scenes);
+  cudaFree(h->d_ids);
+  cudaFree(h->d_scene_ids);
+  delete h;
+  return MG_OK;
+}
+
+int mg_bind_obs(mg_handle* h, void* obs_dev, int64_t nbytes) {
+  if (!h || !obs_dev) return fail(MG_E_INVALID, "mg_bind_obs: null argument%s", "");
+  if (nbytes != h->obs_bytes) return fail(MG_E_INVALID, "mg_bind_obs: buffer size does not match the observation layout%s", "");
+  if (((uintptr_t)obs_dev & 15) != 0) return fail(MG_E_INVALID, "mg_bind_obs: buffer must be 16-byte aligned%s", "");
+  h->obs = (uint8_t*)obs_dev;
+  return MG_OK;
+}
+
+int64_t mg_obs_nbytes(const mg_handle* h) { return h ? h->obs_bytes : -1; }
+
+static int do_raster(mg_handle* h, int only_fresh) {
+  if (!h->obs) return fail(MG_E_STATE, "no observation buffer bound (call mg_bind_obs first)%s", "");
+  CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->cfg.batch, h->res_out, h->ecap,
+                            only_fresh, h->stream));
+  h->launches++;
+  return MG_OK;
+}
+
+int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* scene_ids) {
+  if (!h) return fail(MG_E_INVALID, "mg_reset: null handle%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (!env_ids) n = h->cfg.batch;
+  if (n < 0 || n > h->cfg.batch) return fail(MG_E_INVALID, "mg_reset: bad env count%s", "");
+  if (n == 0) return MG_OK;
+  if (env_ids) {
+    for (int i = 0; i < n; i++)
+      if (env_ids[i] < 0 || env_ids[i] >= h->cfg.batch) return fail(MG_E_INVALID, "mg_reset: env id out of range%s", "");
+    CUDA_TRY(cudaMemcpyAsync(h->d_ids, env_ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (scene_ids) {
+    for (int i = 0; i < n; i++)
+      if (scene_ids[i] < 0 || scene_ids[i] >= h->cfg.n_scenes)
+        return fail(MG_E_INVALID, "mg_reset: scene id out of range%s", "");
+    CUDA_TRY(cudaMemcpyAsync(h->d_scene_ids, scene_ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(mg_launch_reset(h->d_states, h->d_scenes, n, env_ids ? h->d_ids : nullptr,
+                           scene_ids ? h->d_scene_ids : nullptr, 0, h->stream));
+  h->launches++;
+  /* the host arrays may be reused by the caller as soon as we return */
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->obs) return do_raster(h, 1);
+  return MG_OK;
+}
+
+static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
+  if (!actions_dev) return fail(MG_E_INVALID, "mg_step: null actions%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->stream));
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, h->cfg.auto_reset, 0, reward_dev, done_dev,
+                            score_dev, h->stream));
+  h->launches += 2;
+  return MG_OK;
+}
+
+int mg_step(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
+  if (!h) return fail(MG_E_INVALID, "mg_step: null handle%s", "");
+  if (!h->obs) return fail(MG_E_STATE, "mg_step: no observation buffer bound (call mg_bind_obs first)%s", "");
+  int rc = do_physics(h, actions_dev, reward_dev, done_dev, score_dev);
+  if (rc != MG_OK) return rc;
+  return do_raster(h, 0);
+}
+
+int mg_step_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
+  if (!h) return fail(MG_E_INVALID, "mg_step_physics: null handle%s", "");
+  return do_physics(h, actions_dev, reward_dev, done_dev, score_dev);
+}
+
+int mg_render(mg_handle* h) {
+  if (!h) return fail(MG_E_INVALID, "mg_render: null handle%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  return do_raster(h, 0);
+}
+
+int mg_score(mg_handle* h, float* score_dev) {
+  if (!h || !score_dev) return fail(MG_E_INVALID, "mg_score: null argument%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, 0, 1, nullptr, nullptr, score_dev, h->stream));
+  h->launches++;
+  return MG_OK;
+}
+
+int mg_get_state(mg_handle* h, int32_t env, mg_state_t* out) {
+  if (!h || !out) return fail(MG_E_INVALID, "mg_get_state: null argument%s", "");
+  if (env < 0 || env >= h->cfg.batch) return fail(MG_E_INVALID, "mg_get_state: env out of range%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  EnvState st;
+  CUDA_TRY(cudaMemcpyAsync(&st, h->d_states + env, sizeof(EnvState), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  DeviceScene* ds = (DeviceScene*)malloc(sizeof(DeviceScene));
+  if (!ds) return fail(MG_E_NOMEM, "mg_get_state: out of host memory%s", "");
+  cudaError_t e = cudaMemcpy(ds, h->d_scenes + st.scene, sizeof(DeviceScene), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(ds); return fail(MG_E_CUDA, "mg_get_state: %s", cudaGetErrorString(e)); }
+  memset(out, 0, sizeof(*out));
+  out->n_bodies = ds->s.n_bodies;
+  out->n_joints = ds->s.n_joints;
+  out->episode_steps = st.episode_steps;
+  out->scene = st.scene;
+  out->overflow = st.overflow;
+  for (int b = 0; b < ds->s.n_bodies; b++) {
+    out->pos[b][0] = st.P[b].x; out->pos[b][1] = st.P[b].y; out->angle[b] = st.P[b].z;
+    out->vel[b][0] = st.V[b].x; out->vel[b][1] = st.V[b].y; out->angvel[b] = st.V[b].z;
+  }
+  for (int j = 0; j < ds->s.n_joints; j++) { out->joint_acc[j][0] = st.jacc[j].x; out->joint_acc[j][1] = st.jacc[j].y; }
+  int nc = 0;
+  for (int k = 0; k < st.n_arb && k < MG_NARB; k++) {
+    if (st.arb[k].stamp != st.stamp) continue; /* only arbiters that collided in the last sub-step */
+    for (int c = 0; c < st.arb[k].count && nc < 32; c++, nc++) {
+      out->contact_shapes[nc][0] = st.arb[k].a;
+      out->contact_shapes[nc][1] = st.arb[k].b;
+      out->contact_jn[nc] = st.arb[k].jn[c];
+      out->contact_jt[nc] = st.arb[k].jt[c];
+    }
+  }
+  out->n_contacts = nc;
+  free(ds);
+  return MG_OK;
+}
+
+int mg_set_pose(mg_handle* h, int32_t env, int32_t body, double x, double y, double angle) {
+  if (!h) return fail(MG_E_INVALID, "mg_set_pose: null handle%s", "");
+  if (env < 0 || env >= h->cfg.batch || body < 0 || body >= MG_MAX_BODIES)
+    return fail(MG_E_INVALID, "mg_set_pose: index out of range%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  double4 P = make_double4(x, y, angle, 0.0);
+  double sn, cs;
+  mg_det_sincos(angle, &sn, &cs);
+  double2 R = make_double2(cs, sn);
+  EnvState* st = h->d_states + env;
+  CUDA_TRY(cudaMemcpy(&st->P[body], &P, sizeof(P), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(&st->R[body], &R, sizeof(R), cudaMemcpyHostToDevice));
+  return MG_OK;
+}
+
+int64_t mg_launch_count(const mg_handle* h) { return h ? h->launches : 0; }
+
+int mg_synchronize(mg_handle* h) {
+  if (!h) return fail(MG_E_INVALID, "mg_synchronize: null handle%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return MG_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,168 @@
+/*
+ * mg_scene_aux.h — host-side derivation of per-scene constants the kernels
+ * need but the compiled scene does not carry: plane normals, static-shape
+ * bounding boxes, per-joint solver constants and the lane/level schedule that
+ * lets independent joints run on different lanes while keeping the reference's
+ * sequential (Gauss-Seidel) update order bit for bit.
+ *
+ * Reference semantics being prepared for: Chipmunk2D's constraint preStep /
+ * applyImpulse loops inside cpSpaceStep, i.e. `pm.Space.step` at
+ * magical/base_env.py:243 with `space.iterations = 10` (base_env.py:196).
+ */
+#ifndef MG_SCENE_AUX_H
+#define MG_SCENE_AUX_H
+
+#include <math.h>
+#include <string.h>
+
+#include "../../include/magical_b200.h"
+
+#define MG_DT (1.0 / 8.0 / 10.0) /* base_env.py:238-239 at fps=8 (benchmarks/__init__.py:402) */
+#define MG_SUBSTEPS 10           /* base_env.py:237 */
+#define MG_ITERATIONS 10         /* benchmarks/__init__.py:404 */
+#define MG_COLLISION_SLOP 0.01   /* base_env.py:195 */
+#define MG_MAX_LEVELS 32
+
+typedef struct {
+  double cnorm[MG_MAX_CVERTS][2]; /* poly: plane i = edge (v[i-1] -> v[i]); segment: normal at vert0 */
+  float static_bb[MG_MAX_SHAPES][4]; /* conservative fp32 l,b,r,t for shapes on the static body */
+  /* joint solver constants */
+  double j_isum[MG_MAX_JOINTS];   /* gear/spring/limit/motor: 1/(sum of inverse moments); pivot: k diagonal */
+  double j_wcoef[MG_MAX_JOINTS];  /* spring: 1 - exp(-damping*dt/iSum) */
+  double j_bcoef[MG_MAX_JOINTS];  /* bias_coef(error_bias, dt) */
+  double j_jmax[MG_MAX_JOINTS];   /* max_force * dt */
+  /* schedule: joints of level L run concurrently, one per lane */
+  int32_t n_levels;
+  int32_t n_springs;
+  uint8_t sched[MG_MAX_LEVELS][32]; /* joint index or 255 */
+  uint8_t springs[MG_MAX_JOINTS];   /* spring joints in insertion order (their preStep is sequential) */
+  double contact_bias_coef;         /* 1 - pow(collision_bias, dt) */
+  int32_t ok;                       /* 0 if the scene uses a feature the kernels do not implement */
+  int32_t pad_;
+} mg_scene_aux_t;
+
+static inline void mg_aux_norm(double ax, double ay, double bx, double by, double* nx, double* ny) {
+  /* cpvnormalize(cpvrperp(b - a)) */
+  double dx = bx - ax, dy = by - ay;
+  double rx = dy, ry = -dx;
+  double inv = 1.0 / (sqrt(rx * rx + ry * ry) + 2.2250738585072014e-308);
+  *nx = rx * inv;
+  *ny = ry * inv;
+}
+
+static inline const char* mg_build_scene_aux(const mg_scene_t* s, mg_scene_aux_t* aux) {
+  memset(aux, 0, sizeof(*aux));
+  const double dt = MG_DT;
+  if (s->n_bodies < 1 || s->n_bodies > MG_MAX_BODIES) return "bad n_bodies";
+  if (s->n_shapes < 0 || s->n_shapes > MG_MAX_SHAPES) return "bad n_shapes";
+  if (s->n_joints < 0 || s->n_joints > MG_MAX_JOINTS) return "bad n_joints";
+  if (s->n_cgroups < 0 || s->n_cgroups > MG_MAX_CGROUPS) return "bad n_cgroups";
+  if (s->n_bpairs < 0 || s->n_bpairs > MG_MAX_BPAIRS) return "bad n_bpairs";
+  if (s->n_prims < 0 || s->n_prims > MG_MAX_PRIMS) return "bad n_prims";
+  if (s->n_blocks < 0 || s->n_blocks > MG_MAX_BLOCKS) return "bad n_blocks";
+  if (s->n_goals < 0 || s->n_goals > MG_MAX_GOALS) return "bad n_goals";
+  for (int i = 0; i < s->n_shapes; i++) {
+    const mg_shape_t* sh = &s->shapes[i];
+    if (sh->vert0 < 0 || sh->vert0 + sh->nvert > MG_MAX_CVERTS) return "shape vertex range";
+    if (sh->body >= s->n_bodies) return "shape body index";
+    const double(*v)[2] = &s->cverts[sh->vert0];
+    if (sh->kind == MG_SHAPE_SEGMENT) {
+      /* cpSegmentShape: n = rperp(normalize(b - a)) */
+      double dx = v[1][0] - v[0][0], dy = v[1][1] - v[0][1];
+      double inv = 1.0 / (sqrt(dx * dx + dy * dy) + 2.2250738585072014e-308);
+      double ux = dx * inv, uy = dy * inv;
+      aux->cnorm[sh->vert0][0] = uy;
+      aux->cnorm[sh->vert0][1] = -ux;
+    } else if (sh->kind == MG_SHAPE_POLY) {
+      if (sh->nvert < 3 || sh->nvert > 16) return "poly vertex count";
+      for (int k = 0; k < sh->nvert; k++) {
+        int p = (k - 1 + sh->nvert) % sh->nvert;
+        mg_aux_norm(v[p][0], v[p][1], v[k][0], v[k][1], &aux->cnorm[sh->vert0 + k][0], &aux->cnorm[sh->vert0 + k][1]);
+      }
+    } else if (sh->kind != MG_SHAPE_CIRCLE) {
+      return "unknown shape kind";
+    }
+    if (sh->body < 0) {
+      double l = 1e300, r = -1e300, b = 1e300, t = -1e300;
+      for (int k = 0; k < sh->nvert; k++) {
+        if (v[k][0] < l) l = v[k][0];
+        if (v[k][0] > r) r = v[k][0];
+        if (v[k][1] < b) b = v[k][1];
+        if (v[k][1] > t) t = v[k][1];
+      }
+      aux->static_bb[i][0] = nextafterf((float)(l - sh->radius), -INFINITY);
+      aux->static_bb[i][1] = nextafterf((float)(b - sh->radius), -INFINITY);
+      aux->static_bb[i][2] = nextafterf((float)(r + sh->radius), INFINITY);
+      aux->static_bb[i][3] = nextafterf((float)(t + sh->radius), INFINITY);
+    }
+  }
+  /* joints */
+  int last_level[MG_MAX_BODIES];
+  for (int i = 0; i < MG_MAX_BODIES; i++) last_level[i] = 0;
+  int per_level[MG_MAX_LEVELS];
+  for (int i = 0; i < MG_MAX_LEVELS; i++) per_level[i] = 0;
+  memset(aux->sched, 255, sizeof(aux->sched));
+  for (int j = 0; j < s->n_joints; j++) {
+    const mg_joint_t* jt = &s->joints[j];
+    if (jt->a >= s->n_bodies || jt->b >= s->n_bodies || jt->b < 0) return "joint body index";
+    double ia = jt->a < 0 ? 0.0 : s->bodies[jt->a].i_inv;
+    double ib = s->bodies[jt->b].i_inv;
+    double ma = jt->a < 0 ? 0.0 : s->bodies[jt->a].m_inv;
+    double mb = s->bodies[jt->b].m_inv;
+    aux->j_bcoef[j] = 1.0 - pow(jt->error_bias, dt);
+    aux->j_jmax[j] = jt->max_force * dt;
+    switch (jt->kind) {
+      case MG_JOINT_PIVOT: {
+        /* the kernels implement the centre-to-centre pivot only (both anchors at the body
+         * origins), which is the only form the reference creates (entities.py:255, 703) */
+        if (jt->anchor_a[0] != 0.0 || jt->anchor_a[1] != 0.0 || jt->anchor_b[0] != 0.0 || jt->anchor_b[1] != 0.0)
+          return "pivot joints with non-zero anchors are not implemented";
+        if (jt->max_bias != 0.0) return "pivot joints with positional correction are not implemented";
+        double m_sum = ma + mb;
+        double det = m_sum * m_sum - 0.0 * 0.0;
+        double det_inv = 1.0 / det;
+        aux->j_isum[j] = m_sum * det_inv; /* k_tensor diagonal for r1 = r2 = 0 */
+      } break;
+      case MG_JOINT_GEAR: {
+        double ratio = jt->p1, ratio_inv = 1.0 / jt->p1;
+        aux->j_isum[j] = 1.0 / (ia * ratio_inv + ratio * ib);
+      } break;
+      case MG_JOINT_ROTARY_SPRING: {
+        double moment = ia + ib;
+        aux->j_isum[j] = 1.0 / moment;
+        aux->j_wcoef[j] = 1.0 - exp(-jt->p2 * dt * moment);
+        aux->springs[aux->n_springs++] = (uint8_t)j;
+      } break;
+      case MG_JOINT_PIN:
+        break;
+      case MG_JOINT_ROTARY_LIMIT:
+      case MG_JOINT_MOTOR:
+        aux->j_isum[j] = 1.0 / (ia + ib);
+        break;
+      default:
+        return "unknown joint kind";
+    }
+    /* sequential-order-preserving level: one past the latest level of any dynamic body it touches */
+    int lvl = 0;
+    if (jt->a >= 0 && s->bodies[jt->a].kind == MG_BODY_DYNAMIC && last_level[jt->a] > lvl) lvl = last_level[jt->a];
+    if (s->bodies[jt->b].kind == MG_BODY_DYNAMIC && last_level[jt->b] > lvl) lvl = last_level[jt->b];
+    lvl += 1;
+    if (lvl > MG_MAX_LEVELS) return "joint chain too deep";
+    if (jt->a >= 0 && s->bodies[jt->a].kind == MG_BODY_DYNAMIC) last_level[jt->a] = lvl;
+    if (s->bodies[jt->b].kind == MG_BODY_DYNAMIC) last_level[jt->b] = lvl;
+    if (per_level[lvl - 1] >= 32) return "too many joints in one level";
+    aux->sched[lvl - 1][per_level[lvl - 1]++] = (uint8_t)j;
+    if (lvl > aux->n_levels) aux->n_levels = lvl;
+  }
+  for (int g = 0; g < s->n_cgroups; g++) {
+    if (s->cgroups[g].shape0 + s->cgroups[g].nshape > s->n_shapes) return "cgroup shape range";
+  }
+  for (int p = 0; p < s->n_bpairs; p++) {
+    if (s->bpairs[p][0] >= s->n_cgroups || s->bpairs[p][1] >= s->n_cgroups) return "bpair index";
+  }
+  aux->contact_bias_coef = 1.0 - pow(pow(1.0 - 0.1, 60.0), dt);
+  aux->ok = 1;
+  return 0;
+}
+
+#endif /* MG_SCENE_AUX_H */

@@ -1,0 +1,178 @@
+"""Batched, GPU-resident MAGICAL environments.
+
+`MagicalVecEnv` is the batched counterpart of the reference's per-process
+`gym.Env` stack (`BaseEnv.step/reset/render`, magical/base_env.py:177-338,
+wrapped by the LoRes* preprocessors, magical/benchmarks/__init__.py:208-274):
+one object steps `batch` environments of one registered env id on one GPU
+through the C ABI.  PyTorch is used only to own the returned device buffers
+(observation, reward, done, score).
+"""
+import numpy as np
+
+from magical_b200 import _native
+from magical_b200 import scene as sc
+
+PREPROC_TO_MODE = {
+    None: sc.OBS_RAW,
+    'LoRes4E': sc.OBS_LORES4E,
+    'LoRes4A': sc.OBS_LORES4A,
+    'LoRes3EA': sc.OBS_LORES3EA,
+    'LoResStack': sc.OBS_LORESSTACK,
+    'LoResCHW4E': sc.OBS_LORESCHW4E,
+}
+
+
+def obs_shape(mode, batch, res=384):
+    if mode in (sc.OBS_LORES4E, sc.OBS_LORES4A, sc.OBS_LORES3EA):
+        return (batch, 96, 96, 12)
+    if mode == sc.OBS_LORESSTACK:
+        return (2, batch, 96, 96, 12)
+    if mode == sc.OBS_LORESCHW4E:
+        return (batch, 12, 96, 96)
+    return (2, batch, res, res, 3)
+
+
+class MagicalVecEnv:
+    """`batch` environments built by one task object (`task.build_scene()`).
+
+    n_scenes > 1 pre-samples that many scenes from the task's RandomState
+    (needed for the randomised Test* variants); each reset then draws a scene
+    index per environment from `self.rng`.
+    """
+
+    def __init__(self, task, batch, preproc=None, device=0, auto_reset=True,
+                 n_scenes=1, seed=None, scenes=None, stream=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _native.NativeError(
+                "MagicalVecEnv needs a CUDA device: the hot path has no CPU "
+                "implementation in this package")
+        self._torch = torch
+        self._lib = _native.load()
+        self.task = task
+        self.batch = int(batch)
+        self.preproc = preproc
+        self.mode = PREPROC_TO_MODE[preproc]
+        self.device = torch.device('cuda', device)
+        self.auto_reset = bool(auto_reset)
+        self.max_episode_steps = task.max_episode_steps
+        self.rng = np.random.RandomState(seed)
+        if seed is not None:
+            task.seed(seed)
+        if scenes is None:
+            scenes = [task.build_scene() for _ in range(n_scenes)]
+        self.scenes = np.ascontiguousarray(np.stack(scenes)).astype(
+            sc.scene_dt, copy=False)
+        self.n_scenes = len(self.scenes)
+        res = task.res_hw[0]
+        cfg = _native.make_config(device=device, batch=self.batch,
+                                  n_scenes=self.n_scenes, obs_mode=self.mode,
+                                  res=res, auto_reset=int(self.auto_reset),
+                                  fast_math=0)
+        import ctypes
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            self._stream = stream if stream is not None \
+                else torch.cuda.current_stream()
+            _native.check(self._lib.mg_create(
+                cfg.ctypes.data, self.scenes.ctypes.data,
+                ctypes.c_void_p(self._stream.cuda_stream),
+                ctypes.byref(self._h)))
+            self.obs = torch.zeros(obs_shape(self.mode, self.batch, res),
+                                   dtype=torch.uint8, device=self.device)
+            self.reward = torch.zeros(self.batch, dtype=torch.float32,
+                                      device=self.device)
+            self.done = torch.zeros(self.batch, dtype=torch.uint8,
+                                    device=self.device)
+            self.score = torch.zeros(self.batch, dtype=torch.float32,
+                                     device=self.device)
+        _native.check(self._lib.mg_bind_obs(self._h, self.obs.data_ptr(),
+                                            self.obs.numel()))
+
+    # -- gym-like batched API ---------------------------------------------
+    def reset(self, env_ids=None, scene_ids=None):
+        """Reset all (or the given) environments; returns the observation
+        tensor (first frame replicated over the stack)."""
+        ids_p = sid_p = None
+        n = self.batch
+        if env_ids is not None:
+            env_ids = np.ascontiguousarray(env_ids, dtype=np.int32)
+            n = len(env_ids)
+            ids_p = env_ids.ctypes.data
+        if scene_ids is None and self.n_scenes > 1:
+            scene_ids = self.rng.randint(0, self.n_scenes, size=n)
+        if scene_ids is not None:
+            scene_ids = np.ascontiguousarray(scene_ids, dtype=np.int32)
+            assert len(scene_ids) == n
+            sid_p = scene_ids.ctypes.data
+        _native.check(self._lib.mg_reset(self._h, ids_p, n, sid_p))
+        return self.obs
+
+    def step(self, actions):
+        """actions: int32 CUDA tensor [batch] (other int tensors / arrays are
+        converted).  Returns (obs, reward, done, info) with device tensors;
+        info['eval_score'] is non-zero only where done (base_env.py:275-288).
+        The observation tensor is reused between calls."""
+        actions = self._as_actions(actions)
+        _native.check(self._lib.mg_step(
+            self._h, actions.data_ptr(), self.reward.data_ptr(),
+            self.done.data_ptr(), self.score.data_ptr()))
+        return self.obs, self.reward, self.done, {'eval_score': self.score}
+
+    def step_physics(self, actions):
+        """Physics + bookkeeping only (no render)."""
+        actions = self._as_actions(actions)
+        _native.check(self._lib.mg_step_physics(
+            self._h, actions.data_ptr(), self.reward.data_ptr(),
+            self.done.data_ptr(), self.score.data_ptr()))
+        return self.reward, self.done, {'eval_score': self.score}
+
+    def render(self):
+        _native.check(self._lib.mg_render(self._h))
+        return self.obs
+
+    def eval_score(self):
+        """score_on_end_of_traj of every env's current state."""
+        out = self._torch.zeros_like(self.score)
+        _native.check(self._lib.mg_score(self._h, out.data_ptr()))
+        return out
+
+    def _as_actions(self, actions):
+        torch = self._torch
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.int32))
+        if actions.dtype != torch.int32 or actions.device != self.device \
+                or not actions.is_contiguous():
+            actions = actions.to(device=self.device, dtype=torch.int32,
+                                 non_blocking=True).contiguous()
+        assert actions.shape == (self.batch,), actions.shape
+        self._last_actions = actions  # keep alive until the kernels ran
+        return actions
+
+    # -- introspection (tests) --------------------------------------------
+    def get_state(self, env):
+        st = np.zeros((), dtype=sc.state_dt)
+        _native.check(self._lib.mg_get_state(self._h, int(env),
+                                             st.ctypes.data))
+        return st
+
+    def set_pose(self, env, body, x, y, angle):
+        _native.check(self._lib.mg_set_pose(self._h, int(env), int(body),
+                                            float(x), float(y), float(angle)))
+
+    def launch_count(self):
+        return int(self._lib.mg_launch_count(self._h))
+
+    def synchronize(self):
+        _native.check(self._lib.mg_synchronize(self._h))
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.mg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,210 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU
+oracle on identical seeds/actions.  Bars: body pose / velocity / impulses
+BIT-EXACT against the oracle run with the shared deterministic sin/cos, and
+within 1e-9 (north star: 1e-4) against the oracle run with libm sin/cos;
+done masks and pixels bit-exact; scores exact to fp32."""
+import numpy as np
+import pytest
+
+from conftest import demo_tasks, make_demo_task
+
+pytestmark = pytest.mark.gpu
+
+TASKS = list(demo_tasks())
+
+
+def _rollout_compare(task_name, n_steps, batch, seed, det=True, tol=0.0):
+    import torch
+    from magical_b200.vec_env import MagicalVecEnv
+    from oracle_lib import OracleEnv
+    task = make_demo_task(task_name)
+    venv = MagicalVecEnv(task, batch, preproc='LoRes4E', auto_reset=False)
+    venv.reset()
+    rng = np.random.RandomState(seed)
+    actions = rng.randint(0, 18, size=(n_steps, batch)).astype(np.int32)
+    watch = sorted(set([0, batch // 2, batch - 1]))
+    oracles = {e: OracleEnv(venv.scenes[0], det_sincos=det) for e in watch}
+    worst = 0.0
+    max_contacts = 0
+    for t in range(n_steps):
+        rew, done, info = venv.step_physics(torch.from_numpy(actions[t]).cuda())
+        done_h = done.cpu().numpy()
+        score_h = info['eval_score'].cpu().numpy()
+        for e, orc in oracles.items():
+            o_rew, o_done, o_score = orc.step(int(actions[t, e]))
+            st, ost = venv.get_state(e), orc.state()
+            nb, nj = int(st['n_bodies']), int(st['n_joints'])
+            assert int(st['overflow']) == 0
+            for key in ('pos', 'angle', 'vel', 'angvel'):
+                d = np.abs(st[key][:nb] - ost[key][:nb]).max()
+                worst = max(worst, float(d))
+                assert d <= tol, (task_name, t, e, key, d)
+            d = np.abs(st['joint_acc'][:nj] - ost['joint_acc'][:nj]).max()
+            assert d <= tol, (task_name, t, e, 'joint_acc', d)
+            assert int(st['n_contacts']) == int(ost['n_contacts']), (t, e)
+            nc = int(st['n_contacts'])
+            max_contacts = max(max_contacts, nc)
+            if nc:
+                assert np.array_equal(st['contact_shapes'][:nc],
+                                      ost['contact_shapes'][:nc])
+                d = max(np.abs(st['contact_jn'][:nc] - ost['contact_jn'][:nc]).max(),
+                        np.abs(st['contact_jt'][:nc] - ost['contact_jt'][:nc]).max())
+                assert d <= tol, (task_name, t, e, 'contact impulses', d)
+            assert bool(done_h[e]) == o_done, (t, e)
+            assert np.float32(score_h[e]) == np.float32(o_score), (t, e)
+    venv.close()
+    return worst, max_contacts
+
+
+@pytest.mark.parametrize('task_name', TASKS)
+def test_physics_bit_exact_vs_oracle(built, task_name):
+    """All bodies' pose/velocity, joint and contact impulses, done and score:
+    bit-identical to the oracle (deterministic sin/cos) over a full random
+    rollout that runs past the episode end (BaseEnv.step keeps stepping)."""
+    n_steps = {'MoveToRegion': 200}.get(task_name, 130)
+    worst, max_contacts = _rollout_compare(task_name, n_steps, batch=37,
+                                           seed=7, det=True, tol=0.0)
+    assert worst == 0.0
+
+
+def test_config1_pose_within_tolerance_of_libm_oracle(built):
+    """BASELINE config 1: MoveToRegion-Demo, 200 random-action steps; pose of
+    all six robot bodies within 1e-9 of the oracle that uses glibc sin/cos
+    (north-star tolerance: 1e-4)."""
+    worst, _ = _rollout_compare('MoveToRegion', 200, batch=4, seed=42,
+                                det=False, tol=1e-9)
+    print('max |pose/vel delta| vs libm oracle over 200 steps:', worst)
+
+
+def test_contact_rich_rollout_cluster(built):
+    """Scripted actions that drive the robot through the block field so the
+    contact solver, arbiter cache and dependency levels are exercised."""
+    import torch
+    from magical_b200.vec_env import MagicalVecEnv
+    from oracle_lib import OracleEnv
+    task = make_demo_task('ClusterColour')
+    venv = MagicalVecEnv(task, 8, preproc='LoRes4E', auto_reset=False)
+    venv.reset()
+    orc = OracleEnv(venv.scenes[0], det_sincos=True)
+    # forward a lot, with turns: UpOpen=1, UpLeftOpen=4, UpRightClose=16...
+    script = ([1] * 12 + [4] * 6 + [10] * 14 + [16] * 5 + [1] * 20 + [13] * 8
+              + [10] * 25 + [7] * 6 + [1] * 30 + [2] * 10)
+    seen = 0
+    for t, a in enumerate(script):
+        acts = np.full(8, a, dtype=np.int32)
+        venv.step_physics(torch.from_numpy(acts).cuda())
+        orc.step(a)
+        st, ost = venv.get_state(5), orc.state()
+        nb = int(st['n_bodies'])
+        assert np.array_equal(st['pos'][:nb], ost['pos'][:nb]), t
+        assert np.array_equal(st['angle'][:nb], ost['angle'][:nb]), t
+        assert int(st['n_contacts']) == int(ost['n_contacts'])
+        seen = max(seen, int(st['n_contacts']))
+    assert seen >= 2, 'script never produced contacts'
+    venv.close()
+
+
+def _oracle_obs(orc, preproc, frames):
+    """Stack the oracle's per-step lo-res frames like the preprocessors do."""
+    if preproc == 'LoRes4E':
+        return np.concatenate([f['ego'] for f in frames[-4:]], axis=-1)
+    if preproc == 'LoRes4A':
+        return np.concatenate([f['allo'] for f in frames[-4:]], axis=-1)
+    if preproc == 'LoRes3EA':
+        return np.concatenate([frames[-1]['allo']]
+                              + [f['ego'] for f in frames[-3:]], axis=-1)
+    if preproc == 'LoResCHW4E':
+        return np.moveaxis(np.concatenate([f['ego'] for f in frames[-4:]],
+                                          axis=-1), -1, 0)
+    raise ValueError(preproc)
+
+
+@pytest.mark.parametrize('preproc', ['LoRes4E', 'LoRes4A', 'LoRes3EA',
+                                     'LoResCHW4E', 'LoResStack'])
+def test_observation_bit_exact_vs_oracle(built, preproc):
+    """Rasteriser + 4x4 area mean + frame stack against the oracle's
+    brute-force 384x384 render, box filter and explicit stacking."""
+    import torch
+    from magical_b200.vec_env import MagicalVecEnv
+    from oracle_lib import OracleEnv
+    task = make_demo_task('MatchRegions')
+    batch = 5
+    venv = MagicalVecEnv(task, batch, preproc=preproc, auto_reset=False)
+    obs = venv.reset()
+    e = 3
+    orc = OracleEnv(venv.scenes[0], det_sincos=True)
+
+    def oframe():
+        return {'allo': orc.render_lores(0), 'ego': orc.render_lores(1)}
+
+    first = oframe()
+    frames = [first] * 4
+    rng = np.random.RandomState(3)
+
+    def check(obs):
+        obs = obs.cpu().numpy()
+        if preproc == 'LoResStack':
+            want_a = np.concatenate([f['allo'] for f in frames[-4:]], axis=-1)
+            want_e = np.concatenate([f['ego'] for f in frames[-4:]], axis=-1)
+            assert np.array_equal(obs[0, e], want_a)
+            assert np.array_equal(obs[1, e], want_e)
+        else:
+            want = _oracle_obs(orc, preproc, frames)
+            diff = np.abs(obs[e].astype(int) - want.astype(int))
+            assert np.array_equal(obs[e], want), (diff.max(), (diff > 0).sum())
+
+    check(obs)
+    for t in range(12):
+        acts = rng.randint(0, 18, size=batch).astype(np.int32)
+        obs, _, _, _ = venv.step(torch.from_numpy(acts).cuda())
+        orc.step(int(acts[e]))
+        frames.append(oframe())
+        check(obs)
+    venv.close()
+
+
+@pytest.mark.parametrize('task_name', TASKS)
+def test_raw_render_bit_exact_all_tasks(built, task_name):
+    """Full-resolution 384x384 allo + ego frames of every Demo scene after a
+    short rollout: identical to the oracle's brute-force rasteriser."""
+    import torch
+    from magical_b200.vec_env import MagicalVecEnv
+    from oracle_lib import OracleEnv
+    task = make_demo_task(task_name)
+    venv = MagicalVecEnv(task, 2, preproc=None, auto_reset=False)
+    venv.reset()
+    orc = OracleEnv(venv.scenes[0], det_sincos=True)
+    rng = np.random.RandomState(11)
+    for t in range(6):
+        acts = np.full(2, rng.randint(18), dtype=np.int32)
+        obs, _, _, _ = venv.step(torch.from_numpy(acts).cuda())
+        orc.step(int(acts[1]))
+    obs = obs.cpu().numpy()
+    for view in (0, 1):
+        want = orc.render_view(view, 384)
+        diff = np.abs(obs[view, 1].astype(int) - want.astype(int))
+        assert np.array_equal(obs[view, 1], want), \
+            (task_name, view, diff.max(), (diff.max(axis=2) > 0).sum())
+    venv.close()
+
+
+def test_auto_reset_and_done_mask(built):
+    """Episode bookkeeping: done exactly at max_episode_steps, score only on
+    done steps, auto-reset restores the Demo layout and refills the stack."""
+    import torch
+    from magical_b200.vec_env import MagicalVecEnv
+    task = make_demo_task('MoveToRegion')
+    venv = MagicalVecEnv(task, 6, preproc='LoRes4E', auto_reset=True)
+    obs0 = venv.reset().clone()
+    rng = np.random.RandomState(0)
+    for t in range(1, 85):
+        acts = rng.randint(0, 18, size=6).astype(np.int32)
+        obs, rew, done, info = venv.step(torch.from_numpy(acts).cuda())
+        d = done.cpu().numpy()
+        assert np.all(d == (1 if t % 40 == 0 else 0)), t
+        assert float(rew.abs().max()) == 0.0
+        if t % 40 == 0:
+            # first observation of the new episode == reset observation
+            assert torch.equal(obs, obs0)
+            assert int(venv.get_state(2)['episode_steps']) == 0
+    venv.close()
