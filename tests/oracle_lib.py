@@ -52,6 +52,7 @@ def lib():
         L.mgo_block_in_goal.restype = i32
         L.mgo_block_in_goal.argtypes = [vp, i32, i32]
         L.mgo_render_view.argtypes = [vp, i32, i32, vp]
+        L.mgo_collide.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
         L.mgo_downsample4.argtypes = [vp, i32, vp]
         L.mgo_sizeof_scene.restype = ctypes.c_int64
         L.mgo_sizeof_state.restype = ctypes.c_int64
@@ -112,6 +113,20 @@ class OracleEnv:
 
     def block_in_goal(self, block, goal):
         return bool(self._lib.mgo_block_in_goal(self._h, block, goal))
+
+    def collide(self, sa, sb):
+        """Oracle narrowphase for shapes (sa, sb): returns (a, b, n, count,
+        p1[2,2], p2[2,2], hash[2]) with (a, b) in Chipmunk's type order."""
+        ia, ib, cnt = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        n = np.zeros(2)
+        p1 = np.zeros((2, 2))
+        p2 = np.zeros((2, 2))
+        h = np.zeros(2, dtype=np.uint32)
+        self._lib.mgo_collide(self._h, sa, sb, ctypes.byref(ia),
+                              ctypes.byref(ib), n.ctypes.data,
+                              ctypes.byref(cnt), p1.ctypes.data,
+                              p2.ctypes.data, h.ctypes.data)
+        return ia.value, ib.value, n, cnt.value, p1, p2, h
 
     def render_view(self, view, res=384):
         out = np.zeros((res, res, 3), dtype=np.uint8)
