@@ -28,9 +28,9 @@ cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int ba
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
                             const int32_t* scene_ids, int first_time, cudaStream_t stream);
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
-                             int res_out, int ecap, int only_fresh, cudaStream_t stream);
+                             int res_out, int ecap, int scap, int only_fresh, cudaStream_t stream);
 cudaError_t mg_raster_upload_units(const double* units);
-size_t mg_raster_smem_bytes(int mode, int ecap);
+size_t mg_raster_smem_bytes(int mode, int ecap, int scap);
 
 struct mg_handle {
   mg_config_t cfg;
@@ -43,6 +43,7 @@ struct mg_handle {
   int64_t obs_bytes;
   int res_out;
   int ecap;
+  int scap;             /* span-table rows the rasteriser reserves per view */
   int64_t launches;
 };
 
@@ -97,16 +98,43 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
 
   /* derive per-scene constants on the host */
   std::vector<DeviceScene> host(cfg->n_scenes);
-  int ecap = 64;
+  int ecap = 64, scap = 64;
+  const int ss = cfg->obs_mode == MG_OBS_RAW ? 1 : 4;
+  const int res_full = res_out * ss;
+  const double S_full = (double)res_full / 2.04;
   for (int i = 0; i < cfg->n_scenes; i++) {
     host[i].s = scenes[i];
     const char* why = mg_build_scene_aux(&scenes[i], &host[i].aux);
     if (why) return fail(MG_E_INVALID, "mg_create: scene rejected: %s", why);
-    int edges = 0, rprims = 0;
+    int edges = 0, rprims = 0, rows = 0;
     for (int p = 0; p < scenes[i].n_prims; p++) {
       const mg_prim_t& pr = scenes[i].prims[p];
       edges += pr.nvert;
       rprims += pr.kind == MG_PRIM_LINELOOP ? pr.nvert : 1;
+      /* span-table rows: a primitive is rigid, so in any camera it spans at most its diameter */
+      if (pr.kind == MG_PRIM_NGON) {
+        int r = (int)ceil(2.0 * pr.radius * S_full) + 8;
+        rows += r < res_full ? r : res_full;
+      } else if ((int)pr.vert0 + pr.nvert <= MG_MAX_DVERTS) {
+        const float(*dv)[2] = &scenes[i].dverts[pr.vert0];
+        if (pr.kind == MG_PRIM_LINELOOP) {
+          for (int k = 0; k < pr.nvert; k++) {
+            int k2 = (k + 1) % pr.nvert;
+            double len = hypot((double)dv[k][0] - dv[k2][0], (double)dv[k][1] - dv[k2][1]);
+            int r = (int)ceil(len * S_full + pr.radius) + 8;
+            rows += r < res_full ? r : res_full;
+          }
+        } else {
+          double diam = 0.0;
+          for (int a = 0; a < pr.nvert; a++)
+            for (int b = a + 1; b < pr.nvert; b++) {
+              double d = hypot((double)dv[a][0] - dv[b][0], (double)dv[a][1] - dv[b][1]);
+              if (d > diam) diam = d;
+            }
+          int r = (int)ceil(diam * S_full) + 8;
+          rows += r < res_full ? r : res_full;
+        }
+      }
       if (pr.kind == MG_PRIM_NGON && pr.nvert != 10 && pr.nvert != 20 && pr.nvert != 100)
         return fail(MG_E_INVALID, "mg_create: NGON primitives must have 10, 20 or 100 sides%s", "");
       if (pr.kind != MG_PRIM_NGON && (int)pr.vert0 + pr.nvert > MG_MAX_DVERTS)
@@ -114,9 +142,11 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
     }
     if (rprims > 192) return fail(MG_E_INVALID, "mg_create: too many draw primitives in one scene%s", "");
     if (edges > ecap) ecap = edges;
+    if (rows > scap) scap = rows;
   }
   ecap = (ecap + 63) / 64 * 64;
-  if (mg_raster_smem_bytes(cfg->obs_mode, ecap) > 200 * 1024)
+  scap = (scap + 63) / 64 * 64;
+  if (mg_raster_smem_bytes(cfg->obs_mode, ecap, scap) > 200 * 1024)
     return fail(MG_E_INVALID, "mg_create: scene has too many draw edges for the rasteriser's shared memory%s", "");
 
   mg_handle* h = new (std::nothrow) mg_handle();
@@ -126,6 +156,7 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   h->stream = (cudaStream_t)cuda_stream;
   h->res_out = res_out;
   h->ecap = ecap;
+  h->scap = scap;
   h->obs_bytes = obs_bytes_for(cfg, res_out);
   cudaError_t e;
   if ((e = cudaMalloc(&h->d_states, sizeof(EnvState) * (size_t)cfg->batch)) != cudaSuccess ||
@@ -186,7 +217,7 @@ int64_t mg_obs_nbytes(const mg_handle* h) { return h ? h->obs_bytes : -1; }
 static int do_raster(mg_handle* h, int only_fresh) {
   if (!h->obs) return fail(MG_E_STATE, "no observation buffer bound (call mg_bind_obs first)%s", "");
   CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->cfg.batch, h->res_out, h->ecap,
-                            only_fresh, h->stream));
+                            h->scap, only_fresh, h->stream));
   h->launches++;
   return MG_OK;
 }

@@ -305,7 +305,7 @@ __device__ __forceinline__ void joint_apply(EnvSmem& S, const DeviceScene* ds, i
 
 /* ------------------------------------------------------------------ kernel */
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 4)
 k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, const int32_t* __restrict__ actions,
           int batch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -684,6 +684,8 @@ cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const
   size_t smem = mg_physics_smem_bytes(WARPS);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_physics<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_physics<WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured = true;
   }

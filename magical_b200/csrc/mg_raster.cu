@@ -11,20 +11,28 @@
  *                                        benchmarks/__init__.py:139-169, 234
  *   ChannelsFirst                        benchmarks/__init__.py:172-192
  *
- * One CTA per environment.  Phase 1 transforms every draw primitive of the
- * scene into window space for each needed camera (fp32, same operation order
- * as the CPU oracle) and stores edge equations in shared memory.  Phase 2 bins
- * primitives into a 12x12 tile grid (bit masks).  Phase 3: each thread owns
- * groups of 4 consecutive output pixels; per pixel it walks the tile's
- * primitives FRONT TO BACK keeping a 16-bit mask of still-uncovered 4x4
- * sub-samples (the sample grid is exactly the 384x384 frame the reference
- * renders), classifying whole pixels against each edge conservatively and only
- * evaluating individual samples on edges that cross the pixel.  The colour sum
- * of the 16 samples is rounded half-to-even, which is bit-identical to
- * rendering 384x384 and box-filtering (cv2 INTER_AREA).  The 4 pixels' 48
- * bytes of the frame stack are then shifted and rewritten with three 128-bit
- * load/store pairs (HWC layouts), so HBM sees the algorithmic minimum: read
- * the 3 frames that survive, write 4.
+ * One CTA per environment, all in shared memory:
+ *   1. every draw primitive is transformed to window space for each needed
+ *      camera (fp32, the CPU oracle's operation order) -> oriented edge
+ *      equations;
+ *   2. SPAN TABLE: for every (primitive, sample row) the exact interval
+ *      [lo, hi] of covered sample columns.  A sample is covered iff every edge
+ *      function fmaf(A, x, fmaf(B, y, C)) is >= 0; each edge function is
+ *      monotone in x along a row (fp32 rounding is monotone), so the covered
+ *      set is an interval whose ends are found by one division estimate and a
+ *      +-1 correction using the exact expression.  This gives bit-identical
+ *      coverage to brute-force per-sample testing with ~rows x edges work
+ *      instead of pixels x samples x edges;
+ *   3. primitives are binned into a 12x12 tile grid from the spans, together
+ *      with the top-most primitive that covers each tile completely;
+ *   4. half-warps own tiles (uniform control flow); per output pixel the
+ *      primitives are walked FRONT TO BACK, the 4x4 sub-sample mask of a
+ *      primitive is assembled from four span rows with integer ops only, and
+ *      the colour sum of the 16 samples is rounded half-to-even -- identical
+ *      to rendering 384x384 and box filtering (cv2 INTER_AREA);
+ *   5. four pixels = 48 bytes of the frame stack are shifted and rewritten
+ *      with three 128-bit load/store pairs, so HBM sees the algorithmic
+ *      minimum: read the 3 frames that survive, write 4.
  */
 #include "mg_device.cuh"
 
@@ -37,14 +45,13 @@
 #define ZOOM 1.02
 
 struct RPrim {
-  float4 bb;     /* l, b, r, t in sample space (pixels of the res_full frame) */
-  uint32_t rgb;
-  uint16_t e0;   /* first edge / first of 2 float4 describing a line segment */
-  uint16_t ne;   /* edge count (0 for line segments) */
-  float cx, cy;  /* NGON: centre; */
-  float rin, rout; /* NGON: conservative inscribed / circumscribed radii; rout < 0: no accel */
-  float sgn;       /* winding sign of the window-space polygon */
-  float pad_;
+  uint32_t rgb;         /* bits 0..23 colour; bit 24: stippled line */
+  uint16_t e0;          /* first edge (polygons) / first of the 2 float4 of a line segment */
+  uint16_t ne;          /* edge count; 0 = line segment */
+  int16_t row0, nrows;  /* sample rows covered by the bounding box */
+  int16_t col0, col1;   /* sample columns of the bounding box (inclusive) */
+  int32_t span0;        /* offset of this primitive's rows in the span table */
+  float sgn;            /* winding sign of the window-space polygon */
 };
 
 struct Camera {
@@ -111,122 +118,107 @@ __device__ __forceinline__ float2 prim_vertex(const EnvState& st, const mg_scene
 
 struct ViewSmem {
   RPrim* prims;     /* [RMAXP] */
-  float4* edges;    /* [ecap] */
+  float4* edges;    /* [ecap + 2*RMAXP] */
   float2* verts;    /* [ecap] */
+  short2* spans;    /* [scap] (lo, hi) per (primitive, row) */
   uint32_t* tiles;  /* [RGRID*RGRID*RWORDS] */
-  int nrp;
+  int32_t* cover;   /* [RGRID*RGRID] top-most primitive covering the whole tile, -1 = none */
 };
 
-template <int SS>
-__device__ __forceinline__ uint32_t full_mask() { return SS == 4 ? 0xFFFFu : 1u; }
-
-/* coverage mask of window-space primitive `rp` over the SSxSS samples of output pixel (X, Yg) */
-template <int SS>
-__device__ __forceinline__ uint32_t coverage(const RPrim& rp, const float4* __restrict__ edges, int X, int Yg,
-                                             float px_scale) {
-  const float half = 0.5f * (float)SS;            /* pixel centre offset in sample space */
-  const float hext = 0.5f * (float)(SS - 1);      /* max sample offset from the centre */
-  const float x0 = (float)(X * SS), y0 = (float)(Yg * SS);
-  const float xc = x0 + half, yc = y0 + half;
-  /* pixel footprint vs bounding box */
-  if (x0 + (float)SS < rp.bb.x || x0 > rp.bb.z || y0 + (float)SS < rp.bb.y || y0 > rp.bb.w) return 0u;
-  uint32_t mask = full_mask<SS>();
-  if (rp.ne == 0) {
-    /* line segment: (ax, ay, ux, uy), (L, s0, hw, stipple) */
-    float4 p = edges[rp.e0], q = edges[rp.e0 + 1];
-    float rcx = xc - p.x, rcy = yc - p.y;
-    float along_c = fmaf(rcx, p.z, rcy * p.w);
-    float perp_c = fmaf(rcx, p.w, -(rcy * p.z));
-    float reach = hext * 1.4143f + 0.01f;
-    if (fabsf(perp_c) > q.z + reach || along_c < -reach || along_c > q.x + reach) return 0u;
-    uint32_t stipple = __float_as_uint(q.w);
-    uint32_t out = 0u;
-#pragma unroll
-    for (int s = 0; s < SS * SS; s++) {
-      float x = (x0 + (float)(s % SS)) + 0.5f, y = (y0 + (float)(s / SS)) + 0.5f;
-      float rx = x - p.x, ry = y - p.y;
-      float along = fmaf(rx, p.z, ry * p.w);
-      float perp = fmaf(rx, p.w, -(ry * p.z));
-      bool in = !(along < 0.0f || along > q.x || fabsf(perp) > q.z);
-      int bit = ((int)floorf((q.y + along) / px_scale)) & 15;
-      in = in && ((stipple >> bit) & 1u);
-      out |= in ? (1u << s) : 0u;
-    }
-    return out;
-  }
-  if (rp.rout >= 0.0f) {
-    /* many-sided regular polygon: whole-pixel accept/reject against the inscribed/circumscribed circles */
-    float dx = xc - rp.cx, dy = yc - rp.cy;
-    float d = sqrtf(fmaf(dx, dx, dy * dy));
-    float reach = hext * 1.4143f + 0.02f;
-    if (d + reach <= rp.rin) return mask;
-    if (d - reach >= rp.rout) return 0u;
-  }
-  const int e1 = rp.e0 + rp.ne;
-  for (int e = rp.e0; e < e1; e++) {
-    float4 E = edges[e];
-    float ec = fmaf(E.x, xc, fmaf(E.y, yc, E.z));
-    float ext = hext * E.w, margin = 0.01f * E.w;
-    if (ec - ext - margin >= 0.0f) continue;      /* every sample on the inner side */
-    if (ec + ext + margin < 0.0f) return 0u;      /* every sample outside */
-#pragma unroll
-    for (int s = 0; s < SS * SS; s++) {
-      float x = (x0 + (float)(s % SS)) + 0.5f, y = (y0 + (float)(s / SS)) + 0.5f;
-      float v = fmaf(E.x, x, fmaf(E.y, y, E.z));
-      if (!(v >= 0.0f)) mask &= ~(1u << s);
-    }
-    if (mask == 0u) return 0u;
-  }
-  return mask;
+/* first index in [cmin, cmax+1] from which the monotone predicate holds (false...false true...true) */
+template <class F>
+__device__ __forceinline__ int first_true(float est, int cmin, int cmax, F ok) {
+  float e = fminf(fmaxf(est, (float)cmin - 1.0f), (float)cmax + 1.0f);
+  int i = (int)ceilf(e);
+  i = i < cmin ? cmin : (i > cmax + 1 ? cmax + 1 : i);
+  while (i > cmin && ok(i - 1)) i--;
+  while (i <= cmax && !ok(i)) i++;
+  return i;
+}
+/* last index in [cmin-1, cmax] up to which the monotone predicate holds (true...true false...false) */
+template <class F>
+__device__ __forceinline__ int last_true(float est, int cmin, int cmax, F ok) {
+  float e = fminf(fmaxf(est, (float)cmin - 1.0f), (float)cmax + 1.0f);
+  int i = (int)floorf(e);
+  i = i < cmin - 1 ? cmin - 1 : (i > cmax ? cmax : i);
+  while (i < cmax && ok(i + 1)) i++;
+  while (i >= cmin && !ok(i)) i--;
+  return i;
 }
 
-template <int SS>
-__device__ __forceinline__ uint32_t shade(const ViewSmem& vs, int X, int Yg, int tile, float px_scale) {
-  uint32_t unresolved = full_mask<SS>();
-  uint32_t sr = 0, sg = 0, sb = 0;
-  const uint32_t* tm = vs.tiles + tile * RWORDS;
-  for (int w = RWORDS - 1; w >= 0 && unresolved; w--) {
-    uint32_t bits = tm[w];
-    while (bits && unresolved) {
-      int b = 31 - __clz(bits);
-      bits &= ~(1u << b);
-      const RPrim& rp = vs.prims[w * 32 + b];
-      uint32_t m = coverage<SS>(rp, vs.edges, X, Yg, px_scale) & unresolved;
-      if (m) {
-        uint32_t cnt = __popc(m);
-        sr += cnt * (rp.rgb & 0xFF);
-        sg += cnt * ((rp.rgb >> 8) & 0xFF);
-        sb += cnt * ((rp.rgb >> 16) & 0xFF);
-        unresolved &= ~m;
+/* exact covered interval of sample row j for primitive R (empty => lo > hi) */
+__device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restrict__ edges, int j) {
+  int lo = R.col0, hi = R.col1;
+  const float y = (float)j + 0.5f;
+  if (R.ne > 0) {
+    const int e1 = R.e0 + R.ne;
+    for (int e = R.e0; e < e1 && lo <= hi; e++) {
+      float4 E = edges[e];
+      const float A = E.x;
+      const float t = fmaf(E.y, y, E.z);
+      auto ok = [&](int i) { return fmaf(A, (float)i + 0.5f, t) >= 0.0f; };
+      if (A > 0.0f) {
+        lo = first_true(-t / A - 0.5f, lo, hi, ok);
+      } else if (A < 0.0f) {
+        hi = last_true(-t / A - 0.5f, lo, hi, ok);
+      } else if (!(t >= 0.0f)) {
+        hi = lo - 1;
+      }
+    }
+  } else {
+    /* thick line segment: !(along < 0 || along > L || |perp| > hw), each bound monotone in x */
+    float4 p = edges[R.e0], q = edges[R.e0 + 1];
+    const float ry = y - p.y;
+    const float ca = ry * p.w;      /* along = fmaf(rx, ux, ry*uy) */
+    const float cp = -(ry * p.z);   /* perp  = fmaf(rx, uy, -(ry*ux)) */
+    const float ux = p.z, uy = p.w, L = q.x, hw = q.z;
+    auto along = [&](int i) { return fmaf(((float)i + 0.5f) - p.x, ux, ca); };
+    auto perp = [&](int i) { return fmaf(((float)i + 0.5f) - p.x, uy, cp); };
+    if (L < 0.0f) {
+      hi = lo - 1;
+    } else {
+      /* along in [0, L] */
+      if (ux > 0.0f) {
+        lo = first_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
+        if (lo <= hi) hi = last_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
+      } else if (ux < 0.0f) {
+        hi = last_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
+        if (lo <= hi) lo = first_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
+      } else if (ca < 0.0f || ca > L) {
+        hi = lo - 1;
+      }
+      /* perp in [-hw, hw] */
+      if (lo <= hi) {
+        if (uy > 0.0f) {
+          lo = first_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
+          if (lo <= hi) hi = last_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
+        } else if (uy < 0.0f) {
+          hi = last_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
+          if (lo <= hi) lo = first_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
+        } else if (fabsf(cp) > hw) {
+          hi = lo - 1;
+        }
       }
     }
   }
-  if (unresolved) {
-    uint32_t cnt = __popc(unresolved);
-    sr += cnt * BG_R; sg += cnt * BG_G; sb += cnt * BG_B;
-  }
-  if (SS == 4) {
-    /* cv2 INTER_AREA: saturate_cast<uchar>(sum / 16.f) = round half to even */
-    uint32_t q, rem;
-    q = sr >> 4; rem = sr & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sr = q;
-    q = sg >> 4; rem = sg & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sg = q;
-    q = sb >> 4; rem = sb & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sb = q;
-  }
-  return sr | (sg << 8) | (sb << 16);
+  return make_short2((short)lo, (short)hi);
 }
 
-/* Build the window-space primitive set of one view in shared memory. */
-__device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& sc, int view, int res_full, int ecap,
-                           int* s_off /* [MG_MAX_PRIMS+1] */, int* s_misc) {
+/* Build the window-space primitive set, span table and tile bins of one view. */
+template <int SS>
+__device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& sc, int view, int res_out, int ecap,
+                           int scap, int* s_off /* [2*MG_MAX_PRIMS+2] */, int* s_misc) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int np = sc.n_prims;
+  const int res_full = res_out * SS;
   const Camera cam = make_camera(st, sc, view, res_full);
   const float px_scale = (float)res_full / 384.0f;
-  /* A: vertex offsets, window-prim indices (line loops expand to one prim per segment) */
+  /* A: vertex offsets and window-prim indices (a line loop expands to one prim per segment) */
   if (tid == 0) {
     int off = 0, rp = 0;
     for (int p = 0; p < np; p++) {
       s_off[p] = off;
+      s_off[MG_MAX_PRIMS + 1 + p] = rp;
       const mg_prim_t& pr = sc.prims[p];
       off += pr.nvert;
       rp += (pr.kind == MG_PRIM_LINELOOP) ? pr.nvert : 1;
@@ -235,8 +227,11 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     s_misc[0] = off > ecap ? ecap : off;
     s_misc[1] = rp > RMAXP ? RMAXP : rp;
   }
+  for (int i = tid; i < RGRID * RGRID * RWORDS; i += nt) vs.tiles[i] = 0u;
+  for (int i = tid; i < RGRID * RGRID; i += nt) vs.cover[i] = -1;
   __syncthreads();
   const int nv = s_misc[0];
+  const int nrp = s_misc[1];
   /* B: window-space vertices */
   for (int v = tid; v < nv; v += nt) {
     int lo = 0, hi = np - 1;
@@ -244,15 +239,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     vs.verts[v] = prim_vertex(st, sc, sc.prims[lo], v - s_off[lo], cam);
   }
   __syncthreads();
-  /* C: per-primitive records (thread per draw prim; a line loop writes its segments) */
-  if (tid == 0) {
-    int rp = 0;
-    for (int p = 0; p < np; p++) {
-      s_off[MG_MAX_PRIMS + 1 + p] = rp;
-      rp += (sc.prims[p].kind == MG_PRIM_LINELOOP) ? sc.prims[p].nvert : 1;
-    }
-  }
-  __syncthreads();
+  /* C: per-primitive records: bounding box in samples (the oracle's loop bounds), winding */
   for (int p = tid; p < np; p += nt) {
     const mg_prim_t& pr = sc.prims[p];
     int v0 = s_off[p], n = pr.nvert;
@@ -270,16 +257,20 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
           /* a segment's two float4 (ax, ay, ux, uy), (L, s0, hw, stipple) live behind the edge pool */
           RPrim& R = vs.prims[rp0 + k];
           const int slot = ecap + 2 * (rp0 + k);
-          R.rgb = rgb; R.ne = 0; R.e0 = (uint16_t)slot;
-          R.rout = -1.0f; R.rin = 0.0f; R.cx = 0.0f; R.cy = 0.0f; R.sgn = 1.0f;
+          R.rgb = rgb | ((uint32_t)(pr.stipple != 0xFFFF) << 24);
+          R.ne = 0; R.e0 = (uint16_t)slot; R.sgn = 1.0f; R.span0 = 0;
           if (L > 0.0f) {
             float ux = dx / L, uy = dy / L;
-            R.bb = make_float4(fminf(a.x, b.x) - hw - 1.0f, fminf(a.y, b.y) - hw - 1.0f, fmaxf(a.x, b.x) + hw + 1.0f,
-                               fmaxf(a.y, b.y) + hw + 1.0f);
+            float minx = fminf(a.x, b.x) - hw - 1.0f, maxx = fmaxf(a.x, b.x) + hw + 1.0f;
+            float miny = fminf(a.y, b.y) - hw - 1.0f, maxy = fmaxf(a.y, b.y) + hw + 1.0f;
+            int i0 = (int)fmaxf(0.0f, floorf(minx)), i1 = (int)fminf((float)(res_full - 1), ceilf(maxx));
+            int j0 = (int)fmaxf(0.0f, floorf(miny)), j1 = (int)fminf((float)(res_full - 1), ceilf(maxy));
+            R.col0 = (int16_t)i0; R.col1 = (int16_t)i1; R.row0 = (int16_t)j0;
+            R.nrows = (int16_t)((j1 >= j0 && i1 >= i0) ? (j1 - j0 + 1) : 0);
             vs.edges[slot] = make_float4(a.x, a.y, ux, uy);
             vs.edges[slot + 1] = make_float4(L, s0, hw, __uint_as_float((uint32_t)pr.stipple));
           } else {
-            R.bb = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
+            R.col0 = 0; R.col1 = -1; R.row0 = 0; R.nrows = 0;
             vs.edges[slot] = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
             vs.edges[slot + 1] = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
           }
@@ -295,23 +286,27 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         area2 += a.x * c.y - a.y * c.x;
         l = fminf(l, a.x); r = fmaxf(r, a.x); b = fminf(b, a.y); t = fmaxf(t, a.y);
       }
-      R.bb = make_float4(l - 1.0f, b - 1.0f, r + 1.0f, t + 1.0f);
+      int i0 = (int)fmaxf(0.0f, floorf(l - 1.0f)), i1 = (int)fminf((float)(res_full - 1), ceilf(r + 1.0f));
+      int j0 = (int)fmaxf(0.0f, floorf(b - 1.0f)), j1 = (int)fminf((float)(res_full - 1), ceilf(t + 1.0f));
       R.rgb = rgb;
-      R.sgn = (area2 >= 0.0f) ? 1.0f : -1.0f; /* winding sign consumed in phase D */
-      R.e0 = (uint16_t)v0; R.ne = (uint16_t)n;
-      R.rout = -1.0f; R.rin = 0.0f; R.cx = 0.0f; R.cy = 0.0f;
-      if (pr.kind == MG_PRIM_NGON && n >= 20) {
-        /* centre = mean of opposite vertices; radii from the window-space scale */
-        float2 a = vs.verts[v0], c = vs.verts[v0 + n / 2];
-        R.cx = 0.5f * (a.x + c.x); R.cy = 0.5f * (a.y + c.y);
-        float rad = pr.radius * cam.S;
-        R.rout = rad * 1.001f + 0.05f;
-        R.rin = rad * cospif(1.0f / (float)n) * 0.999f - 0.05f;
-      }
+      R.sgn = (area2 >= 0.0f) ? 1.0f : -1.0f;
+      R.e0 = (uint16_t)v0; R.ne = (uint16_t)n; R.span0 = 0;
+      R.col0 = (int16_t)i0; R.col1 = (int16_t)i1; R.row0 = (int16_t)j0;
+      R.nrows = (int16_t)((j1 >= j0 && i1 >= i0) ? (j1 - j0 + 1) : 0);
     }
   }
   __syncthreads();
-  /* D: edge equations, oriented so that inside is >= 0 */
+  /* D: span-table offsets (serial prefix; <= 192 entries) + oriented edge equations */
+  if (tid == 0) {
+    int off = 0;
+    for (int p = 0; p < nrp; p++) {
+      RPrim& R = vs.prims[p];
+      if (off + R.nrows > scap) R.nrows = 0; /* cannot happen with the host's bound; keeps memory safe */
+      R.span0 = off;
+      off += R.nrows;
+    }
+    s_misc[2] = off;
+  }
   for (int v = tid; v < nv; v += nt) {
     int lo = 0, hi = np - 1;
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= v) lo = mid; else hi = mid - 1; }
@@ -324,38 +319,133 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     float sgn = vs.prims[rp0].sgn;
     float A = a.y - b.y, B = b.x - a.x;
     float C = -fmaf(A, a.x, B * a.y);
-    A *= sgn; B *= sgn; C *= sgn;
-    vs.edges[v] = make_float4(A, B, C, fabsf(A) + fabsf(B));
+    vs.edges[v] = make_float4(A * sgn, B * sgn, C * sgn, 0.0f);
   }
   __syncthreads();
-  vs.nrp = s_misc[1];
+  /* E: spans, one work item per (primitive, row) */
+  const int nspan = s_misc[2];
+  for (int w = tid; w < nspan; w += nt) {
+    int lo = 0, hi = nrp - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (vs.prims[mid].span0 <= w) lo = mid; else hi = mid - 1; }
+    const RPrim& R = vs.prims[lo];
+    vs.spans[w] = row_span(R, vs.edges, R.row0 + (w - R.span0));
+  }
+  __syncthreads();
+  /* F: tile bins from the spans: one work item per (primitive, tile row) */
+  const int TS = (res_out / RGRID) * SS; /* samples per tile side */
+  for (int w = tid; w < nrp * RGRID; w += nt) {
+    int p = w / RGRID, ty = w % RGRID;
+    const RPrim& R = vs.prims[p];
+    if (R.nrows == 0) continue;
+    int ja = ty * TS, jb = ja + TS - 1;
+    int a = max(ja, (int)R.row0), b = min(jb, R.row0 + R.nrows - 1);
+    if (a > b) continue;
+    int umin = 32767, umax = -1;   /* hull of the covered columns */
+    int cmin = -1, cmax = 32767;   /* columns covered by EVERY row of the tile row */
+    bool all_rows = (a == ja && b == jb);
+    for (int j = a; j <= b; j++) {
+      short2 s = vs.spans[R.span0 + (j - R.row0)];
+      if (s.x <= s.y) {
+        umin = min(umin, (int)s.x); umax = max(umax, (int)s.y);
+        cmin = max(cmin, (int)s.x); cmax = min(cmax, (int)s.y);
+      } else {
+        all_rows = false;
+      }
+    }
+    if (umax < umin) continue;
+    const bool solid = (R.rgb >> 24) == 0; /* stippled segments never cover a tile completely */
+    for (int tx = umin / TS; tx <= umax / TS && tx < RGRID; tx++) {
+      atomicOr(&vs.tiles[(ty * RGRID + tx) * RWORDS + (p >> 5)], 1u << (p & 31));
+      if (all_rows && solid && cmin <= tx * TS && cmax >= tx * TS + TS - 1) atomicMax(&vs.cover[ty * RGRID + tx], p);
+    }
+  }
+  __syncthreads();
 }
 
+/* colour of output pixel (X, Yg): front-to-back walk over the tile's primitives */
 template <int SS>
-__device__ void bin_tiles(ViewSmem& vs, int res_out) {
-  const int T = res_out / RGRID; /* output pixels per tile side */
-  for (int w = threadIdx.x; w < RGRID * RGRID * RWORDS; w += blockDim.x) {
-    int tile = w / RWORDS, word = w % RWORDS;
-    int tx = tile % RGRID, ty = tile / RGRID; /* ty counts GL rows (bottom-up) */
-    float l = (float)(tx * T * SS), r = (float)((tx + 1) * T * SS);
-    float b = (float)(ty * T * SS), t = (float)((ty + 1) * T * SS);
-    uint32_t bits = 0;
-    for (int i = 0; i < 32; i++) {
-      int p = word * 32 + i;
-      if (p >= vs.nrp) break;
-      float4 bb = vs.prims[p].bb;
-      bool hit = !(bb.z < l || bb.x > r || bb.w < b || bb.y > t);
-      if (hit && vs.prims[p].ne == 0) {
-        /* thick segment vs tile: distance of the tile centre from the segment's line */
-        float4 sg = vs.edges[vs.prims[p].e0], sq = vs.edges[vs.prims[p].e0 + 1];
-        float cxm = 0.5f * (l + r) - sg.x, cym = 0.5f * (b + t) - sg.y;
-        float perp = fabsf(fmaf(cxm, sg.w, -(cym * sg.z)));
-        float halfdiag = 0.7072f * (r - l) + 1.0f;
-        hit = perp <= sq.z + halfdiag;
+__device__ __forceinline__ uint32_t shade(const ViewSmem& vs, int X, int Yg, int tile, float px_scale) {
+  constexpr uint32_t FULLM = (SS == 4) ? 0xFFFFu : 1u;
+  constexpr uint32_t ROWM = (1u << SS) - 1u;
+  uint32_t unresolved = FULLM;
+  uint32_t sr = 0, sg = 0, sb = 0;
+  const uint32_t* tm = vs.tiles + tile * RWORDS;
+  const int cover = vs.cover[tile];
+  const int x0 = X * SS, y0 = Yg * SS;
+  for (int w = RWORDS - 1; w >= 0 && unresolved; w--) {
+    uint32_t bits = tm[w];
+    if (cover >= 0 && (cover >> 5) == w) bits &= ~((1u << (cover & 31)) - 1u); /* nothing shows through it */
+    while (bits && unresolved) {
+      int b = 31 - __clz(bits);
+      bits &= ~(1u << b);
+      const int p = w * 32 + b;
+      const RPrim& R = vs.prims[p];
+      uint32_t m;
+      if (p == cover) {
+        m = unresolved;
+      } else {
+        m = 0u;
+#pragma unroll
+        for (int r = 0; r < SS; r++) {
+          int row = y0 + r - R.row0;
+          if (row >= 0 && row < R.nrows) {
+            short2 s = vs.spans[R.span0 + row];
+            int l = max((int)s.x - x0, 0), h = min((int)s.y - x0, SS - 1);
+            if (l <= h) m |= ((ROWM >> (SS - 1 - (h - l))) << l) << (SS * r);
+          }
+        }
+        m &= unresolved;
+        if (m && (R.rgb >> 24)) {
+          /* stippled line: GL stipple bit from the distance along the loop, per covered sample */
+          float4 pp = vs.edges[R.e0], q = vs.edges[R.e0 + 1];
+          uint32_t stipple = __float_as_uint(q.w);
+          uint32_t keep = 0u, mm = m;
+          while (mm) {
+            int s = __ffs(mm) - 1;
+            mm &= mm - 1;
+            float x = ((float)(x0 + (s % SS))) + 0.5f, y = ((float)(y0 + (s / SS))) + 0.5f;
+            float along = fmaf(x - pp.x, pp.z, (y - pp.y) * pp.w);
+            int bit = ((int)floorf((q.y + along) / px_scale)) & 15;
+            keep |= ((stipple >> bit) & 1u) << s;
+          }
+          m = keep;
+        }
       }
-      bits |= hit ? (1u << i) : 0u;
+      if (m) {
+        uint32_t cnt = __popc(m);
+        sr += cnt * (R.rgb & 0xFF);
+        sg += cnt * ((R.rgb >> 8) & 0xFF);
+        sb += cnt * ((R.rgb >> 16) & 0xFF);
+        unresolved &= ~m;
+      }
     }
-    vs.tiles[w] = bits;
+    if (cover >= 0 && (cover >> 5) == w) break;
+  }
+  if (unresolved) {
+    uint32_t cnt = __popc(unresolved);
+    sr += cnt * BG_R; sg += cnt * BG_G; sb += cnt * BG_B;
+  }
+  if (SS == 4) {
+    /* cv2 INTER_AREA: saturate_cast<uchar>(sum / 16.f) = round half to even */
+    uint32_t q, rem;
+    q = sr >> 4; rem = sr & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sr = q;
+    q = sg >> 4; rem = sg & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sg = q;
+    q = sb >> 4; rem = sb & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sb = q;
+  }
+  return sr | (sg << 8) | (sb << 16);
+}
+
+/* shift one pixel's 12 stack bytes left by one frame and append colour n (or replicate when fresh) */
+__device__ __forceinline__ void stack_push(uint32_t* w, uint32_t n, bool fresh) {
+  if (fresh) {
+    w[0] = n | (n << 24);
+    w[1] = (n >> 8) | (n << 16);
+    w[2] = (n >> 16) | (n << 8);
+  } else {
+    uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    w[0] = (w0 >> 24) | (w1 << 8);
+    w[1] = (w1 >> 24) | (w2 << 8);
+    w[2] = (w2 >> 24) | (n << 8);
   }
 }
 
@@ -364,7 +454,7 @@ __device__ void bin_tiles(ViewSmem& vs, int res_out) {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, uint8_t* __restrict__ obs, int batch,
-         int res_out, int ecap, int only_fresh) {
+         int res_out, int ecap, int scap, int only_fresh) {
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
   constexpr int NV = (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESCHW4E) ? 1 : 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -376,104 +466,68 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   const EnvState& st = stg;
   if (only_fresh && st.fresh == 0) return; /* block-uniform: after mg_reset only the reset envs are redrawn */
   const mg_scene_t& sc = scenes[st.scene].s;
-  const int res_full = res_out * SS;
-  const float px_scale = (float)res_full / 384.0f;
+  const float px_scale = (float)(res_out * SS) / 384.0f;
 
-  /* carve shared memory: per view [prims | edges (+ segment slots) | verts | tiles] */
+  /* carve shared memory per view */
   ViewSmem vsm[NV];
   {
     unsigned char* p = smem_raw;
     for (int v = 0; v < NV; v++) {
       vsm[v].edges = reinterpret_cast<float4*>(p); p += sizeof(float4) * (size_t)(ecap + 2 * RMAXP);
-      vsm[v].prims = reinterpret_cast<RPrim*>(p); p += sizeof(RPrim) * RMAXP;
       vsm[v].verts = reinterpret_cast<float2*>(p); p += sizeof(float2) * (size_t)ecap;
+      vsm[v].prims = reinterpret_cast<RPrim*>(p); p += sizeof(RPrim) * RMAXP;
+      vsm[v].spans = reinterpret_cast<short2*>(p); p += sizeof(short2) * (size_t)scap;
       vsm[v].tiles = reinterpret_cast<uint32_t*>(p); p += sizeof(uint32_t) * RGRID * RGRID * RWORDS;
+      vsm[v].cover = reinterpret_cast<int32_t*>(p); p += sizeof(int32_t) * RGRID * RGRID;
     }
   }
   for (int v = 0; v < NV; v++) {
     int view = (NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1);
-    build_view(vsm[v], st, sc, view, res_full, ecap, s_off, s_misc);
-    bin_tiles<SS>(vsm[v], res_out);
+    build_view<SS>(vsm[v], st, sc, view, res_out, ecap, scap, s_off, s_misc);
     __syncthreads();
   }
   const bool fresh = st.fresh != 0;
-  const int T = res_out / RGRID;
-  const int groups_per_row = res_out / 4;
-  const int n_groups = groups_per_row * res_out;
+  const int T = res_out / RGRID;        /* output pixels per tile side (multiple of 4) */
+  const int gpr = T / 4;                /* 4-pixel groups per tile row */
+  const int gpt = gpr * T;              /* groups per tile */
   const size_t frame_px = (size_t)res_out * res_out;
+  /* half-warps own tiles: all 16 lanes walk the same primitive list */
+  const int hw_id = threadIdx.x >> 4, hl = threadIdx.x & 15;
+  const int n_hw = blockDim.x >> 4;
 
-  for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
-    const int Y = g / groups_per_row;        /* output row, 0 = top */
-    const int X0 = (g % groups_per_row) * 4;
-    const int Yg = res_out - 1 - Y;          /* GL row (bottom-up) */
-    const int tile = (Yg / T) * RGRID + X0 / T;
-    uint32_t col[NV][4];
+  for (int tile = hw_id; tile < RGRID * RGRID; tile += n_hw) {
+    const int tx = tile % RGRID, ty = tile / RGRID; /* ty counts GL rows (bottom-up) */
+    for (int g = hl; g < gpt; g += 16) {
+      const int Yg = ty * T + g / gpr;
+      const int X0 = tx * T + (g % gpr) * 4;
+      const int Y = res_out - 1 - Yg;       /* output row, 0 = top */
+      uint32_t col[NV][4];
 #pragma unroll
-    for (int v = 0; v < NV; v++)
+      for (int v = 0; v < NV; v++)
 #pragma unroll
-      for (int i = 0; i < 4; i++) col[v][i] = shade<SS>(vsm[v], X0 + i, Yg, tile, px_scale);
+        for (int i = 0; i < 4; i++) col[v][i] = shade<SS>(vsm[v], X0 + i, Yg, tile, px_scale);
 
-    if (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A) {
-      /* [B, R, R, 12]: 4 pixels = 48 bytes = 3 x uint4; shift every pixel's 12 bytes left by 3 */
-      uint4* ptr = reinterpret_cast<uint4*>(obs + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
-      uint32_t w[12];
-      if (!fresh) {
-        uint4 a = ptr[0], b = ptr[1], c = ptr[2];
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-        w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
-      }
+      if (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK) {
+        /* [B, R, R, 12] (LoResStack: [2, B, R, R, 12]): 4 pixels = 48 bytes = 3 x uint4 */
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        uint32_t n = col[0][i];
-        if (fresh) {
-          /* frame replicated over the stack (FlattenFrameStack.reset, benchmarks/__init__.py:130-136) */
-          w[3 * i] = n | (n << 24);
-          w[3 * i + 1] = (n >> 8) | (n << 16);
-          w[3 * i + 2] = (n >> 16) | (n << 8);
-        } else {
-          uint32_t w0 = w[3 * i], w1 = w[3 * i + 1], w2 = w[3 * i + 2];
-          w[3 * i] = (w0 >> 24) | (w1 << 8);
-          w[3 * i + 1] = (w1 >> 24) | (w2 << 8);
-          w[3 * i + 2] = (w2 >> 24) | (n << 8);
+        for (int v = 0; v < NV; v++) {
+          size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)v * batch : 0;
+          uint4* ptr = reinterpret_cast<uint4*>(obs + ((plane + env) * frame_px + (size_t)Y * res_out + X0) * 12);
+          uint32_t w[12];
+          if (!fresh) {
+            uint4 a = ptr[0], b = ptr[1], c = ptr[2];
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) stack_push(&w[3 * i], col[v][i], fresh);
+          ptr[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          ptr[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          ptr[2] = make_uint4(w[8], w[9], w[10], w[11]);
         }
-      }
-      ptr[0] = make_uint4(w[0], w[1], w[2], w[3]);
-      ptr[1] = make_uint4(w[4], w[5], w[6], w[7]);
-      ptr[2] = make_uint4(w[8], w[9], w[10], w[11]);
-    } else if (MODE == MG_OBS_LORES3EA) {
-      /* bytes 0..2 = newest allo frame; bytes 3..11 = 3 ego frames, oldest first */
-      uint4* ptr = reinterpret_cast<uint4*>(obs + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
-      uint32_t w[12];
-      if (!fresh) {
-        uint4 a = ptr[0], b = ptr[1], c = ptr[2];
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-        w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        uint32_t al = col[0][i], eg = col[1][i];
-        if (fresh) {
-          w[3 * i] = al | (eg << 24);
-          w[3 * i + 1] = (eg >> 8) | (eg << 16);
-          w[3 * i + 2] = (eg >> 16) | (eg << 8);
-        } else {
-          uint32_t w1 = w[3 * i + 1], w2 = w[3 * i + 2];
-          /* old bytes 6..11 -> 3..8 ; new ego -> 9..11 */
-          uint32_t b6 = (w1 >> 16) & 0xFF, b7 = (w1 >> 24) & 0xFF;
-          w[3 * i] = al | (b6 << 24);
-          w[3 * i + 1] = b7 | (w2 << 8);
-          w[3 * i + 2] = (w2 >> 24) | (eg << 8);
-        }
-      }
-      ptr[0] = make_uint4(w[0], w[1], w[2], w[3]);
-      ptr[1] = make_uint4(w[4], w[5], w[6], w[7]);
-      ptr[2] = make_uint4(w[8], w[9], w[10], w[11]);
-    } else if (MODE == MG_OBS_LORESSTACK) {
-      /* [2, B, R, R, 12] */
-#pragma unroll
-      for (int v = 0; v < NV; v++) {
-        uint4* ptr = reinterpret_cast<uint4*>(
-            obs + (((size_t)v * batch + env) * frame_px + (size_t)Y * res_out + X0) * 12);
+      } else if (MODE == MG_OBS_LORES3EA) {
+        /* bytes 0..2 = newest allo frame; bytes 3..11 = 3 ego frames, oldest first */
+        uint4* ptr = reinterpret_cast<uint4*>(obs + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
         uint32_t w[12];
         if (!fresh) {
           uint4 a = ptr[0], b = ptr[1], c = ptr[2];
@@ -482,46 +536,47 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
         }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          uint32_t n = col[v][i];
+          uint32_t al = col[0][i], eg = col[NV - 1][i];
           if (fresh) {
-            w[3 * i] = n | (n << 24);
-            w[3 * i + 1] = (n >> 8) | (n << 16);
-            w[3 * i + 2] = (n >> 16) | (n << 8);
+            w[3 * i] = al | (eg << 24);
+            w[3 * i + 1] = (eg >> 8) | (eg << 16);
+            w[3 * i + 2] = (eg >> 16) | (eg << 8);
           } else {
-            uint32_t w0 = w[3 * i], w1 = w[3 * i + 1], w2 = w[3 * i + 2];
-            w[3 * i] = (w0 >> 24) | (w1 << 8);
-            w[3 * i + 1] = (w1 >> 24) | (w2 << 8);
-            w[3 * i + 2] = (w2 >> 24) | (n << 8);
+            uint32_t w1 = w[3 * i + 1], w2 = w[3 * i + 2];
+            uint32_t b6 = (w1 >> 16) & 0xFF, b7 = (w1 >> 24) & 0xFF;
+            w[3 * i] = al | (b6 << 24);          /* old bytes 6..11 -> 3..8 ; new ego -> 9..11 */
+            w[3 * i + 1] = b7 | (w2 << 8);
+            w[3 * i + 2] = (w2 >> 24) | (eg << 8);
           }
         }
         ptr[0] = make_uint4(w[0], w[1], w[2], w[3]);
         ptr[1] = make_uint4(w[4], w[5], w[6], w[7]);
         ptr[2] = make_uint4(w[8], w[9], w[10], w[11]);
-      }
-    } else if (MODE == MG_OBS_LORESCHW4E) {
-      /* [B, 12, R, R]: plane c of frame f is channel 3f + c; 4 pixels = one u32 per plane */
-      uint8_t* base = obs + (size_t)env * 12 * frame_px + (size_t)Y * res_out + X0;
+      } else if (MODE == MG_OBS_LORESCHW4E) {
+        /* [B, 12, R, R]: plane c of frame f is channel 3f + c; 4 pixels = one u32 per plane */
+        uint8_t* base = obs + (size_t)env * 12 * frame_px + (size_t)Y * res_out + X0;
 #pragma unroll
-      for (int c = 0; c < 3; c++) {
-        uint32_t nw = ((col[0][0] >> (8 * c)) & 0xFF) | (((col[0][1] >> (8 * c)) & 0xFF) << 8) |
-                      (((col[0][2] >> (8 * c)) & 0xFF) << 16) | (((col[0][3] >> (8 * c)) & 0xFF) << 24);
-        uint32_t* p0 = reinterpret_cast<uint32_t*>(base + (size_t)(0 + c) * frame_px);
-        uint32_t* p1 = reinterpret_cast<uint32_t*>(base + (size_t)(3 + c) * frame_px);
-        uint32_t* p2 = reinterpret_cast<uint32_t*>(base + (size_t)(6 + c) * frame_px);
-        uint32_t* p3 = reinterpret_cast<uint32_t*>(base + (size_t)(9 + c) * frame_px);
-        if (fresh) { *p0 = nw; *p1 = nw; *p2 = nw; *p3 = nw; }
-        else { uint32_t a = *p1, b = *p2, d = *p3; *p0 = a; *p1 = b; *p2 = d; *p3 = nw; }
-      }
-    } else {
-      /* RAW [2, B, R, R, 3]: 4 pixels = 12 bytes = 3 x u32 */
+        for (int c = 0; c < 3; c++) {
+          uint32_t nw = ((col[0][0] >> (8 * c)) & 0xFF) | (((col[0][1] >> (8 * c)) & 0xFF) << 8) |
+                        (((col[0][2] >> (8 * c)) & 0xFF) << 16) | (((col[0][3] >> (8 * c)) & 0xFF) << 24);
+          uint32_t* p0 = reinterpret_cast<uint32_t*>(base + (size_t)(0 + c) * frame_px);
+          uint32_t* p1 = reinterpret_cast<uint32_t*>(base + (size_t)(3 + c) * frame_px);
+          uint32_t* p2 = reinterpret_cast<uint32_t*>(base + (size_t)(6 + c) * frame_px);
+          uint32_t* p3 = reinterpret_cast<uint32_t*>(base + (size_t)(9 + c) * frame_px);
+          if (fresh) { *p0 = nw; *p1 = nw; *p2 = nw; *p3 = nw; }
+          else { uint32_t a = *p1, b = *p2, d = *p3; *p0 = a; *p1 = b; *p2 = d; *p3 = nw; }
+        }
+      } else {
+        /* RAW [2, B, R, R, 3]: 4 pixels = 12 bytes = 3 x u32 */
 #pragma unroll
-      for (int v = 0; v < NV; v++) {
-        uint32_t* ptr = reinterpret_cast<uint32_t*>(
-            obs + (((size_t)v * batch + env) * frame_px + (size_t)Y * res_out + X0) * 3);
-        uint32_t c0 = col[v][0], c1 = col[v][1], c2 = col[v][2], c3 = col[v][3];
-        ptr[0] = c0 | (c1 << 24);
-        ptr[1] = (c1 >> 8) | (c2 << 16);
-        ptr[2] = (c2 >> 16) | (c3 << 8);
+        for (int v = 0; v < NV; v++) {
+          uint32_t* ptr = reinterpret_cast<uint32_t*>(
+              obs + (((size_t)v * batch + env) * frame_px + (size_t)Y * res_out + X0) * 3);
+          uint32_t c0 = col[v][0], c1 = col[v][1], c2 = col[v][2], c3 = col[v][3];
+          ptr[0] = c0 | (c1 << 24);
+          ptr[1] = (c1 >> 8) | (c2 << 16);
+          ptr[2] = (c2 >> 16) | (c3 << 8);
+        }
       }
     }
   }
@@ -529,11 +584,15 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   if (threadIdx.x == 0 && fresh) stg.fresh = 0;
 }
 
-size_t mg_raster_smem_bytes(int mode, int ecap) {
-  int nv = (mode == MG_OBS_LORES4E || mode == MG_OBS_LORES4A || mode == MG_OBS_LORESCHW4E) ? 1 : 2;
-  size_t per_view = sizeof(float4) * (size_t)(ecap + 2 * RMAXP) + sizeof(RPrim) * RMAXP + sizeof(float2) * (size_t)ecap +
-                    sizeof(uint32_t) * RGRID * RGRID * RWORDS;
-  return per_view * nv;
+static int n_views(int mode) {
+  return (mode == MG_OBS_LORES4E || mode == MG_OBS_LORES4A || mode == MG_OBS_LORESCHW4E) ? 1 : 2;
+}
+
+size_t mg_raster_smem_bytes(int mode, int ecap, int scap) {
+  size_t per_view = sizeof(float4) * (size_t)(ecap + 2 * RMAXP) + sizeof(float2) * (size_t)ecap + sizeof(RPrim) * RMAXP +
+                    sizeof(short2) * (size_t)scap + sizeof(uint32_t) * RGRID * RGRID * RWORDS +
+                    sizeof(int32_t) * RGRID * RGRID;
+  return per_view * n_views(mode);
 }
 
 cudaError_t mg_raster_upload_units(const double* units /* [130][2] */) {
@@ -542,23 +601,25 @@ cudaError_t mg_raster_upload_units(const double* units /* [130][2] */) {
 
 template <int MODE>
 static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch, int res_out,
-                               int ecap, int only_fresh, cudaStream_t stream) {
-  size_t smem = mg_raster_smem_bytes(MODE, ecap);
+                               int ecap, int scap, int only_fresh, cudaStream_t stream) {
+  size_t smem = mg_raster_smem_bytes(MODE, ecap, scap);
   cudaError_t e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_raster<MODE><<<batch, 256, smem, stream>>>(states, scenes, obs, batch, res_out, ecap, only_fresh);
+  e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  k_raster<MODE><<<batch, 256, smem, stream>>>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh);
   return cudaGetLastError();
 }
 
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
-                             int res_out, int ecap, int only_fresh, cudaStream_t stream) {
+                             int res_out, int ecap, int scap, int only_fresh, cudaStream_t stream) {
   switch (mode) {
-    case MG_OBS_LORES4E: return launch_mode<MG_OBS_LORES4E>(states, scenes, obs, batch, res_out, ecap, only_fresh, stream);
-    case MG_OBS_LORES4A: return launch_mode<MG_OBS_LORES4A>(states, scenes, obs, batch, res_out, ecap, only_fresh, stream);
-    case MG_OBS_LORES3EA: return launch_mode<MG_OBS_LORES3EA>(states, scenes, obs, batch, res_out, ecap, only_fresh, stream);
-    case MG_OBS_LORESSTACK: return launch_mode<MG_OBS_LORESSTACK>(states, scenes, obs, batch, res_out, ecap, only_fresh, stream);
-    case MG_OBS_LORESCHW4E: return launch_mode<MG_OBS_LORESCHW4E>(states, scenes, obs, batch, res_out, ecap, only_fresh, stream);
-    case MG_OBS_RAW: return launch_mode<MG_OBS_RAW>(states, scenes, obs, batch, res_out, ecap, only_fresh, stream);
+    case MG_OBS_LORES4E: return launch_mode<MG_OBS_LORES4E>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
+    case MG_OBS_LORES4A: return launch_mode<MG_OBS_LORES4A>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
+    case MG_OBS_LORES3EA: return launch_mode<MG_OBS_LORES3EA>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
+    case MG_OBS_LORESSTACK: return launch_mode<MG_OBS_LORESSTACK>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
+    case MG_OBS_LORESCHW4E: return launch_mode<MG_OBS_LORESCHW4E>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
+    case MG_OBS_RAW: return launch_mode<MG_OBS_RAW>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
   }
   return cudaErrorInvalidValue;
 }
