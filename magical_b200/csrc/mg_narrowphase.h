@@ -267,6 +267,7 @@ MG_HD SupEdge support_edge_segment(const ShapeView& seg, d2 n) {
 
 struct Manifold {
   d2 n;
+  double margin; /* separation left between the shapes when they do not touch (<= 0: unknown / touching) */
   int count;
   d2 p1[2], p2[2];
   unsigned hash[2];
@@ -308,6 +309,7 @@ MG_HD void contact_points(SupEdge e1, SupEdge e2, const ClosestPts& points, Mani
 MG_HD void mg_collide(const ShapeView& a, const ShapeView& b, const double* bba, const double* bbb, Manifold& m) {
   m.count = 0;
   m.n = D2(0, 0);
+  m.margin = -1.0;
   if (a.kind == 0 && b.kind == 0) {
     double mindist = a.radius + b.radius;
     d2 ca = sv_vert(a, 0), cb = sv_vert(b, 0);
@@ -317,6 +319,8 @@ MG_HD void mg_collide(const ShapeView& a, const ShapeView& b, const double* bba,
       double dist = sqrt(distsq);
       d2 n = m.n = (dist ? dmul(delta, 1.0 / dist) : D2(1.0, 0.0));
       manifold_push(m, dadd(ca, dmul(n, a.radius)), dadd(cb, dmul(n, -b.radius)), 0);
+    } else {
+      m.margin = sqrt(distsq) - mindist;
     }
   } else if (a.kind == 0 && b.kind == 1) {
     d2 seg_a = sv_vert(b, 0), seg_b = sv_vert(b, 1), center = sv_vert(a, 0);
@@ -330,21 +334,29 @@ MG_HD void mg_collide(const ShapeView& a, const ShapeView& b, const double* bba,
       double dist = sqrt(distsq);
       d2 n = m.n = (dist ? dmul(delta, 1.0 / dist) : sv_normal(b, 0));
       manifold_push(m, dadd(center, dmul(n, a.radius)), dadd(closest, dmul(n, -b.radius)), 0);
+    } else {
+      m.margin = sqrt(distsq) - mindist;
     }
   } else if (a.kind == 0 && b.kind == 2) {
     ClosestPts pts = mg_gjk(a, b, bba, bbb);
     if (pts.d <= a.radius + b.radius) {
       d2 n = m.n = pts.n;
       manifold_push(m, dadd(pts.a, dmul(n, a.radius)), dadd(pts.b, dmul(n, -b.radius)), 0);
+    } else {
+      m.margin = pts.d - (a.radius + b.radius);
     }
   } else if (a.kind == 1 && b.kind == 2) {
     ClosestPts pts = mg_gjk(a, b, bba, bbb);
     if (pts.d - a.radius - b.radius <= 0.0)
       contact_points(support_edge_segment(a, pts.n), support_edge_poly(b, dneg(pts.n)), pts, m);
+    else
+      m.margin = pts.d - a.radius - b.radius;
   } else if (a.kind == 2 && b.kind == 2) {
     ClosestPts pts = mg_gjk(a, b, bba, bbb);
     if (pts.d - a.radius - b.radius <= 0.0)
       contact_points(support_edge_poly(a, pts.n), support_edge_poly(b, dneg(pts.n)), pts, m);
+    else
+      m.margin = pts.d - a.radius - b.radius;
   }
 }
 

@@ -31,25 +31,40 @@ struct __align__(16) ConSmem {
   double r1x, r1y, r2x, r2y, nx, ny, jn, jt;
   double u;
   uint32_t hash;
-  uint8_t ba, bb; /* body indices, 255 = static */
+  uint8_t ba, bb; /* body slots, 16 = static */
   uint8_t arb, slot;
   uint8_t first;
   uint8_t pad_[7];
 };
 
+/* Separation cache: a pair whose shapes were measured `margin` apart cannot touch before the two bodies
+ * have moved that far.  `limit` is the value of (path[a] + path[b]) at which the measurement expires. */
+struct SepEntry {
+  uint8_t a, b;
+  uint16_t pad_;
+  float limit;
+};
+#define MG_NSEP 32
+#define SLOT_STATIC MG_MAX_BODIES /* velocity slot of the static body: always reads as zero */
+
 struct __align__(16) EnvSmem {
   EnvState st; /* staged copy of the HBM record */
-  double2 MI[MG_MAX_BODIES]; /* m_inv, i_inv */
+  double4 V[MG_MAX_BODIES + 1];  /* working velocities (vx, vy, w); slot 16 = static body */
+  double4 Bv[MG_MAX_BODIES + 1]; /* working bias velocities */
+  double2 MI[MG_MAX_BODIES + 1]; /* m_inv, i_inv (0 for static / kinematic) */
   double jdyn[MG_MAX_JOINTS][8]; /* per-sub-step joint data (bias / rate / pin frame) */
   float4 sbb[MG_MAX_SHAPES];     /* conservative fp32 shape boxes (l, b, r, t) */
   float4 gbb[MG_MAX_CGROUPS];    /* collision-group boxes */
   ConSmem con[MG_NCON];
   ArbEntry arb2[MG_NARB];
+  SepEntry sep[MG_NSEP];
+  float path[MG_MAX_BODIES + 1]; /* upper bound of the distance any point of the body has moved this launch */
   uint8_t cand[MG_NCAND][2];
-  uint8_t blevel[MG_MAX_BODIES];
+  uint8_t blevel[MG_MAX_BODIES + 1];
   uint8_t clevel[MG_NCON];
   int32_t max_clevel;
-  int32_t pad_[3];
+  int32_t n_sep;
+  int32_t pad_[2];
 };
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -85,79 +100,59 @@ __device__ __forceinline__ ShapeView make_view(const EnvSmem& S, const DeviceSce
   return v;
 }
 
-/* velocity access with static (255 / <0) bodies reading as zero */
-struct Vel { double vx, vy, w; };
-__device__ __forceinline__ Vel ld_vel(const EnvSmem& S, int b) {
-  Vel r;
-  if (b >= 0 && b < MG_MAX_BODIES) { double4 t = S.st.V[b]; r.vx = t.x; r.vy = t.y; r.w = t.z; }
-  else { r.vx = 0.0; r.vy = 0.0; r.w = 0.0; }
-  return r;
-}
-__device__ __forceinline__ Vel ld_bias(const EnvSmem& S, int b) {
-  Vel r;
-  if (b >= 0 && b < MG_MAX_BODIES) { double4 t = S.st.Bv[b]; r.vx = t.x; r.vy = t.y; r.w = t.z; }
-  else { r.vx = 0.0; r.vy = 0.0; r.w = 0.0; }
-  return r;
-}
-/* apply_impulse(body, j, r): v += j*m_inv; w += i_inv * cross(r, j).  Bodies with zero inverse mass
- * (static, kinematic) are left untouched: the update would add exactly zero. */
+/* apply_impulse(body, j, r): v += j*m_inv; w += i_inv * cross(r, j).  Branch-free: static and kinematic
+ * bodies carry zero inverse mass, so the update adds exactly zero to them. */
 __device__ __forceinline__ void apply_imp(EnvSmem& S, int b, double m_inv, double i_inv, double jx, double jy,
                                           double rx, double ry) {
-  if (b < 0 || b >= MG_MAX_BODIES || (m_inv == 0.0 && i_inv == 0.0)) return;
-  double4 t = S.st.V[b];
+  double4 t = S.V[b];
   t.x = t.x + jx * m_inv;
   t.y = t.y + jy * m_inv;
   t.z += i_inv * (rx * jy - ry * jx);
-  S.st.V[b] = t;
+  S.V[b] = t;
 }
 __device__ __forceinline__ void apply_bias_imp(EnvSmem& S, int b, double m_inv, double i_inv, double jx, double jy,
                                                double rx, double ry) {
-  if (b < 0 || b >= MG_MAX_BODIES || (m_inv == 0.0 && i_inv == 0.0)) return;
-  double4 t = S.st.Bv[b];
+  double4 t = S.Bv[b];
   t.x = t.x + jx * m_inv;
   t.y = t.y + jy * m_inv;
   t.z += i_inv * (rx * jy - ry * jx);
-  S.st.Bv[b] = t;
+  S.Bv[b] = t;
 }
-__device__ __forceinline__ void add_w(EnvSmem& S, int b, double dw) {
-  if (b < 0 || b >= MG_MAX_BODIES) return;
-  S.st.V[b].z += dw;
-}
-__device__ __forceinline__ void sub_w(EnvSmem& S, int b, double dw) {
-  if (b < 0 || b >= MG_MAX_BODIES) return;
-  S.st.V[b].z -= dw;
-}
-__device__ __forceinline__ double2 ld_mi(const EnvSmem& S, int b) {
-  if (b >= 0 && b < MG_MAX_BODIES) return S.MI[b];
-  return make_double2(0.0, 0.0);
-}
-__device__ __forceinline__ double ld_angle(const EnvSmem& S, int b) { return (b >= 0) ? S.st.P[b].z : 0.0; }
-__device__ __forceinline__ bool is_dyn(const EnvSmem& S, int b) {
-  return b >= 0 && b < MG_MAX_BODIES && (S.MI[b].x != 0.0 || S.MI[b].y != 0.0);
-}
+__device__ __forceinline__ double ld_angle(const EnvSmem& S, int b) { return (b < MG_MAX_BODIES) ? S.st.P[b].z : 0.0; }
 
 /* ------------------------------------------------------------------ joints */
+struct JC {
+  double ma, ia, mb, ib, c0, c1, c2, c3;
+};
+__device__ __forceinline__ JC ld_jc(const DeviceScene* ds, int j) {
+  const double2* p = reinterpret_cast<const double2*>(&ds->aux.jc[j][0]);
+  double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+  JC r;
+  r.ma = a.x; r.ia = a.y; r.mb = b.x; r.ib = b.y; r.c0 = c.x; r.c1 = c.y; r.c2 = d.x; r.c3 = d.y;
+  return r;
+}
+
 __device__ __forceinline__ void joint_prestep(EnvSmem& S, const DeviceScene* ds, int j) {
   const mg_joint_t& J = ds->s.joints[j];
   const double dt = MG_DT;
-  int a = J.a, b = J.b;
-  switch (J.kind) {
+  const int a = ds->aux.ja[j], b = ds->aux.jb[j];
+  switch (ds->aux.jkind[j]) {
     case MG_JOINT_GEAR: {
       double maxBias = J.max_bias;
       double ratio = J.p1;
       S.jdyn[j][0] = dclamp(-ds->aux.j_bcoef[j] * (ld_angle(S, b) * ratio - ld_angle(S, a) - J.p0) / dt, -maxBias, maxBias);
     } break;
     case MG_JOINT_PIN: {
-      double2 Ra = (a >= 0) ? S.st.R[a] : make_double2(1.0, 0.0);
+      double2 Ra = (a < MG_MAX_BODIES) ? S.st.R[a] : make_double2(1.0, 0.0);
       double2 Rb = S.st.R[b];
       d2 r1 = D2(Ra.x * J.anchor_a[0] - Ra.y * J.anchor_a[1], Ra.y * J.anchor_a[0] + Ra.x * J.anchor_a[1]);
       d2 r2 = D2(Rb.x * J.anchor_b[0] - Rb.y * J.anchor_b[1], Rb.y * J.anchor_b[0] + Rb.x * J.anchor_b[1]);
-      d2 pa = (a >= 0) ? D2(S.st.P[a].x, S.st.P[a].y) : D2(0, 0);
+      d2 pa = (a < MG_MAX_BODIES) ? D2(S.st.P[a].x, S.st.P[a].y) : D2(0, 0);
       d2 pb = D2(S.st.P[b].x, S.st.P[b].y);
       d2 delta = dsub(dadd(pb, r2), dadd(pa, r1));
       double dist = dlength(delta);
       d2 n = dmul(delta, 1.0 / (dist ? dist : MG_INF));
-      double2 ma = ld_mi(S, a), mb = ld_mi(S, b);
+      double2 ma = S.MI[a], mb = S.MI[b];
       double rcn1 = dcross(r1, n), rcn2 = dcross(r2, n);
       double k = (ma.x + ma.y * rcn1 * rcn1) + (mb.x + mb.y * rcn2 * rcn2);
       double maxBias = J.max_bias;
@@ -183,122 +178,120 @@ __device__ __forceinline__ void joint_prestep(EnvSmem& S, const DeviceScene* ds,
 
 __device__ __forceinline__ void spring_prestep(EnvSmem& S, const DeviceScene* ds, int j) {
   const mg_joint_t& J = ds->s.joints[j];
-  int a = J.a, b = J.b;
+  const int a = ds->aux.ja[j], b = ds->aux.jb[j];
   S.jdyn[j][0] = 0.0; /* target_wrn */
   double j_spring = ((ld_angle(S, a) - ld_angle(S, b)) - J.p0) * J.p1 * MG_DT;
   S.st.jacc[j].x = j_spring;
-  sub_w(S, a, j_spring * ld_mi(S, a).y);
-  add_w(S, b, j_spring * ld_mi(S, b).y);
+  S.V[a].z -= j_spring * S.MI[a].y;
+  S.V[b].z += j_spring * S.MI[b].y;
 }
 
 __device__ __forceinline__ void joint_warm(EnvSmem& S, const DeviceScene* ds, int j) {
-  const mg_joint_t& J = ds->s.joints[j];
-  int a = J.a, b = J.b;
-  double2 ma = ld_mi(S, a), mb = ld_mi(S, b);
+  const int a = ds->aux.ja[j], b = ds->aux.jb[j];
+  const JC c = ld_jc(ds, j);
   double2 acc = S.st.jacc[j];
-  switch (J.kind) {
+  switch (ds->aux.jkind[j]) {
     case MG_JOINT_PIVOT:
-      apply_imp(S, a, ma.x, ma.y, -acc.x, -acc.y, 0.0, 0.0);
-      apply_imp(S, b, mb.x, mb.y, acc.x, acc.y, 0.0, 0.0);
+      apply_imp(S, a, c.ma, c.ia, -acc.x, -acc.y, 0.0, 0.0);
+      apply_imp(S, b, c.mb, c.ib, acc.x, acc.y, 0.0, 0.0);
       break;
-    case MG_JOINT_GEAR: {
-      double jj = acc.x;
-      if (is_dyn(S, a)) sub_w(S, a, jj * ma.y * (1.0 / J.p1));
-      if (is_dyn(S, b)) add_w(S, b, jj * mb.y);
-    } break;
+    case MG_JOINT_GEAR:
+      S.V[a].z -= acc.x * c.ia * c.c3;
+      S.V[b].z += acc.x * c.ib;
+      break;
     case MG_JOINT_PIN: {
       double jx = S.jdyn[j][4] * acc.x, jy = S.jdyn[j][5] * acc.x;
-      apply_imp(S, a, ma.x, ma.y, -jx, -jy, S.jdyn[j][0], S.jdyn[j][1]);
-      apply_imp(S, b, mb.x, mb.y, jx, jy, S.jdyn[j][2], S.jdyn[j][3]);
+      apply_imp(S, a, c.ma, c.ia, -jx, -jy, S.jdyn[j][0], S.jdyn[j][1]);
+      apply_imp(S, b, c.mb, c.ib, jx, jy, S.jdyn[j][2], S.jdyn[j][3]);
     } break;
     case MG_JOINT_ROTARY_LIMIT:
-    case MG_JOINT_MOTOR: {
-      double jj = acc.x;
-      if (is_dyn(S, a)) sub_w(S, a, jj * ma.y);
-      if (is_dyn(S, b)) add_w(S, b, jj * mb.y);
-    } break;
+    case MG_JOINT_MOTOR:
+      S.V[a].z -= acc.x * c.ia;
+      S.V[b].z += acc.x * c.ib;
+      break;
     default:
       break;
   }
 }
 
 __device__ __forceinline__ void joint_apply(EnvSmem& S, const DeviceScene* ds, int j) {
-  const mg_joint_t& J = ds->s.joints[j];
-  int a = J.a, b = J.b;
-  double2 ma = ld_mi(S, a), mb = ld_mi(S, b);
-  switch (J.kind) {
+  const int a = ds->aux.ja[j], b = ds->aux.jb[j];
+  const JC c = ld_jc(ds, j);
+  switch (ds->aux.jkind[j]) {
     case MG_JOINT_PIVOT: {
-      Vel va = ld_vel(S, a), vb = ld_vel(S, b);
-      double kd = ds->aux.j_isum[j];
-      double jx = (0.0 - (vb.vx - va.vx)) * kd;
-      double jy = (0.0 - (vb.vy - va.vy)) * kd;
+      double4 va = S.V[a], vb = S.V[b];
+      double jx = (0.0 - (vb.x - va.x)) * c.c0;
+      double jy = (0.0 - (vb.y - va.y)) * c.c0;
       double2 old = S.st.jacc[j];
-      d2 acc = dvclamp(D2(old.x + jx, old.y + jy), ds->aux.j_jmax[j]);
+      d2 acc = dvclamp(D2(old.x + jx, old.y + jy), c.c1);
       S.st.jacc[j] = make_double2(acc.x, acc.y);
       jx = acc.x - old.x; jy = acc.y - old.y;
-      apply_imp(S, a, ma.x, ma.y, -jx, -jy, 0.0, 0.0);
-      apply_imp(S, b, mb.x, mb.y, jx, jy, 0.0, 0.0);
+      /* anchors are at the body origins: no angular part (adds exactly zero) */
+      va.x = va.x + (-jx) * c.ma; va.y = va.y + (-jy) * c.ma;
+      vb.x = vb.x + jx * c.mb; vb.y = vb.y + jy * c.mb;
+      S.V[a] = va;
+      S.V[b] = vb;
     } break;
     case MG_JOINT_GEAR: {
-      double ratio = J.p1, ratio_inv = 1.0 / J.p1;
-      double wr = ld_vel(S, b).w * ratio - ld_vel(S, a).w;
-      double jMax = ds->aux.j_jmax[j];
-      double jj = (S.jdyn[j][0] - wr) * ds->aux.j_isum[j];
+      double wr = S.V[b].z * c.c2 - S.V[a].z;
+      double jj = (S.jdyn[j][0] - wr) * c.c0;
       double jOld = S.st.jacc[j].x;
-      double jNew = dclamp(jOld + jj, -jMax, jMax);
+      double jNew = dclamp(jOld + jj, -c.c1, c.c1);
       S.st.jacc[j].x = jNew;
       jj = jNew - jOld;
-      if (is_dyn(S, a)) sub_w(S, a, jj * ma.y * ratio_inv);
-      if (is_dyn(S, b)) add_w(S, b, jj * mb.y);
+      S.V[a].z -= jj * c.ia * c.c3;
+      S.V[b].z += jj * c.ib;
     } break;
     case MG_JOINT_ROTARY_SPRING: {
-      double wrn = ld_vel(S, a).w - ld_vel(S, b).w;
-      double w_damp = (S.jdyn[j][0] - wrn) * ds->aux.j_wcoef[j];
+      double wrn = S.V[a].z - S.V[b].z;
+      double w_damp = (S.jdyn[j][0] - wrn) * c.c2;
       S.jdyn[j][0] = wrn + w_damp;
-      double j_damp = w_damp * ds->aux.j_isum[j];
+      double j_damp = w_damp * c.c0;
       S.st.jacc[j].x += j_damp;
-      if (is_dyn(S, a)) add_w(S, a, j_damp * ma.y);
-      if (is_dyn(S, b)) sub_w(S, b, j_damp * mb.y);
+      S.V[a].z += j_damp * c.ia;
+      S.V[b].z -= j_damp * c.ib;
     } break;
     case MG_JOINT_PIN: {
       d2 r1 = D2(S.jdyn[j][0], S.jdyn[j][1]), r2 = D2(S.jdyn[j][2], S.jdyn[j][3]);
       d2 n = D2(S.jdyn[j][4], S.jdyn[j][5]);
-      Vel va = ld_vel(S, a), vb = ld_vel(S, b);
-      d2 v1 = dadd(D2(va.vx, va.vy), dmul(dperp(r1), va.w));
-      d2 v2 = dadd(D2(vb.vx, vb.vy), dmul(dperp(r2), vb.w));
+      double4 va = S.V[a], vb = S.V[b];
+      d2 v1 = dadd(D2(va.x, va.y), dmul(dperp(r1), va.z));
+      d2 v2 = dadd(D2(vb.x, vb.y), dmul(dperp(r2), vb.z));
       double vrn = ddot(dsub(v2, v1), n);
-      double jnMax = ds->aux.j_jmax[j];
       double jn = (S.jdyn[j][7] - vrn) * S.jdyn[j][6];
       double jnOld = S.st.jacc[j].x;
-      double jnNew = dclamp(jnOld + jn, -jnMax, jnMax);
+      double jnNew = dclamp(jnOld + jn, -c.c1, c.c1);
       S.st.jacc[j].x = jnNew;
       jn = jnNew - jnOld;
-      apply_imp(S, a, ma.x, ma.y, -(n.x * jn), -(n.y * jn), r1.x, r1.y);
-      apply_imp(S, b, mb.x, mb.y, n.x * jn, n.y * jn, r2.x, r2.y);
+      double jx = n.x * jn, jy = n.y * jn;
+      va.x = va.x + (-jx) * c.ma; va.y = va.y + (-jy) * c.ma;
+      va.z += c.ia * (r1.x * (-jy) - r1.y * (-jx));
+      vb.x = vb.x + jx * c.mb; vb.y = vb.y + jy * c.mb;
+      vb.z += c.ib * (r2.x * jy - r2.y * jx);
+      S.V[a] = va;
+      S.V[b] = vb;
     } break;
     case MG_JOINT_ROTARY_LIMIT: {
       double bias = S.jdyn[j][0];
       if (!bias) return;
-      double wr = ld_vel(S, b).w - ld_vel(S, a).w;
-      double jMax = ds->aux.j_jmax[j];
-      double jj = -(bias + wr) * ds->aux.j_isum[j];
+      double wr = S.V[b].z - S.V[a].z;
+      double jj = -(bias + wr) * c.c0;
       double jOld = S.st.jacc[j].x;
-      double jNew = (bias < 0.0) ? dclamp(jOld + jj, 0.0, jMax) : dclamp(jOld + jj, -jMax, 0.0);
+      double jNew = (bias < 0.0) ? dclamp(jOld + jj, 0.0, c.c1) : dclamp(jOld + jj, -c.c1, 0.0);
       S.st.jacc[j].x = jNew;
       jj = jNew - jOld;
-      if (is_dyn(S, a)) sub_w(S, a, jj * ma.y);
-      if (is_dyn(S, b)) add_w(S, b, jj * mb.y);
+      S.V[a].z -= jj * c.ia;
+      S.V[b].z += jj * c.ib;
     } break;
     case MG_JOINT_MOTOR: {
-      double wr = ld_vel(S, b).w - ld_vel(S, a).w + S.jdyn[j][0];
-      double jMax = ds->aux.j_jmax[j];
-      double jj = -wr * ds->aux.j_isum[j];
+      double wr = S.V[b].z - S.V[a].z + S.jdyn[j][0];
+      double jj = -wr * c.c0;
       double jOld = S.st.jacc[j].x;
-      double jNew = dclamp(jOld + jj, -jMax, jMax);
+      double jNew = dclamp(jOld + jj, -c.c1, c.c1);
       S.st.jacc[j].x = jNew;
       jj = jNew - jOld;
-      if (is_dyn(S, a)) sub_w(S, a, jj * ma.y);
-      if (is_dyn(S, b)) add_w(S, b, jj * mb.y);
+      S.V[a].z -= jj * c.ia;
+      S.V[b].z += jj * c.ib;
     } break;
   }
 }
@@ -330,9 +323,13 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
   const DeviceScene* ds = scenes + S.st.scene;
   const mg_scene_t& sc = ds->s;
   const int nb = sc.n_bodies, ns = sc.n_shapes, nj = sc.n_joints, ncg = sc.n_cgroups, nbp = sc.n_bpairs;
-  if (lane < MG_MAX_BODIES) {
+  if (lane <= MG_MAX_BODIES) {
     S.MI[lane] = (lane < nb) ? make_double2(sc.bodies[lane].m_inv, sc.bodies[lane].i_inv) : make_double2(0.0, 0.0);
+    S.V[lane] = (lane < MG_MAX_BODIES) ? S.st.V[lane] : make_double4(0.0, 0.0, 0.0, 0.0);
+    S.Bv[lane] = (lane < MG_MAX_BODIES) ? S.st.Bv[lane] : make_double4(0.0, 0.0, 0.0, 0.0);
+    S.path[lane] = 0.0f;
   }
+  int n_sep = 0;
   const double dt = MG_DT;
 
   /* ---- Robot.set_action: id = 9*grip + 3*lr + ud (entities.py:162-186, 439-457) */
@@ -361,10 +358,10 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
       Pc.z = S.st.P[robot].z + rel_turn;
       S.st.P[control] = Pc;
       double2 Rb = S.st.R[robot];
-      double4 Vc = S.st.V[control];
+      double4 Vc = S.V[control];
       Vc.x = Rb.x * 0.0 - Rb.y * target_speed;
       Vc.y = Rb.x * target_speed + Rb.y * 0.0;
-      S.st.V[control] = Vc;
+      S.V[control] = Vc;
     } else if (lane <= 2) {
       int f = lane - 1;
       double side = (f == 0) ? -1.0 : 1.0;
@@ -378,7 +375,7 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
 
     /* ---- integrate positions (cpBodyUpdatePosition; kinematic control body included) */
     if (lane < nb) {
-      double4 P = S.st.P[lane], V = S.st.V[lane], Bv = S.st.Bv[lane];
+      double4 P = S.st.P[lane], V = S.V[lane], Bv = S.Bv[lane];
       P.x = P.x + (V.x + Bv.x) * dt;
       P.y = P.y + (V.y + Bv.y) * dt;
       P.z = P.z + (V.z + Bv.z) * dt;
@@ -386,7 +383,10 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
       mg_det_sincos(P.z, &sn, &cs);
       S.st.P[lane] = P;
       S.st.R[lane] = make_double2(cs, sn);
-      S.st.Bv[lane] = make_double4(0.0, 0.0, 0.0, 0.0);
+      S.Bv[lane] = make_double4(0.0, 0.0, 0.0, 0.0);
+      /* how far can any point of this body's shapes have moved: |dp|_1 + reach * |dtheta|, rounded up */
+      double moved = (fabs(V.x + Bv.x) + fabs(V.y + Bv.y) + ds->aux.body_reach[lane] * fabs(V.z + Bv.z)) * dt;
+      S.path[lane] = __fadd_ru(S.path[lane], __double2float_ru(moved * 1.000001));
     }
     __syncwarp();
 
@@ -453,14 +453,41 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
       Manifold m;
       m.count = 0;
       int ia = 0, ib = 0;
+      int sep_slot = -1;        /* existing separation-cache entry of this pair */
+      float sep_limit = -1.0f;  /* > 0: (re)write the entry with this expiry */
+      bool skipped = false;     /* cached separation still valid: narrowphase not run */
       if (c < ncand) {
         ia = S.cand[c][0]; ib = S.cand[c][1];
         if (sc.shapes[ia].kind > sc.shapes[ib].kind) { int t = ia; ia = ib; ib = t; }
-        ShapeView va = make_view(S, ds, ia), vb = make_view(S, ds, ib);
-        double bba[4], bbb[4];
-        sv_bb(va, bba);
-        sv_bb(vb, bbb);
-        if (bb_intersects(bba, bbb)) mg_collide(va, vb, bba, bbb, m);
+        const int sba = sc.shapes[ia].body < 0 ? SLOT_STATIC : sc.shapes[ia].body;
+        const int sbb = sc.shapes[ib].body < 0 ? SLOT_STATIC : sc.shapes[ib].body;
+        const float travelled = __fadd_ru(S.path[sba], S.path[sbb]);
+        for (int k = 0; k < n_sep; k++)
+          if (S.sep[k].a == ia && S.sep[k].b == ib) { sep_slot = k; skipped = travelled < S.sep[k].limit; }
+        if (!skipped) {
+          ShapeView va = make_view(S, ds, ia), vb = make_view(S, ds, ib);
+          double bba[4], bbb[4];
+          sv_bb(va, bba);
+          sv_bb(vb, bbb);
+          if (bb_intersects(bba, bbb)) {
+            mg_collide(va, vb, bba, bbb, m);
+            /* shapes `margin` apart cannot touch until the bodies have travelled that far */
+            if (m.count == 0 && m.margin > 1e-6)
+              sep_limit = __fadd_rd(travelled, __double2float_rd(m.margin * 0.999999 - 1e-9));
+          }
+        }
+      }
+      {
+        /* update the separation cache (existing entries in place, new ones appended in lane order) */
+        unsigned want_new = __ballot_sync(FULL, sep_limit > 0.0f && sep_slot < 0);
+        if (sep_limit > 0.0f) {
+          int k = sep_slot >= 0 ? sep_slot : n_sep + __popc(want_new & ((1u << lane) - 1u));
+          if (k < MG_NSEP) { S.sep[k].a = (uint8_t)ia; S.sep[k].b = (uint8_t)ib; S.sep[k].pad_ = 0; S.sep[k].limit = sep_limit; }
+        } else if (sep_slot >= 0 && !skipped) {
+          S.sep[sep_slot].limit = -1.0f; /* measured again: touching, or too close to cache */
+        }
+        n_sep = min(n_sep + __popc(want_new), MG_NSEP);
+        __syncwarp();
       }
       unsigned has = __ballot_sync(FULL, m.count > 0);
       int arb_idx = narb_new + __popc(has & ((1u << lane) - 1u));
@@ -472,6 +499,8 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
           int ba = sc.shapes[ia].body, bb = sc.shapes[ib].body;
           d2 pa = (ba >= 0) ? D2(S.st.P[ba].x, S.st.P[ba].y) : D2(0, 0);
           d2 pb = (bb >= 0) ? D2(S.st.P[bb].x, S.st.P[bb].y) : D2(0, 0);
+          if (ba < 0) ba = SLOT_STATIC;
+          if (bb < 0) bb = SLOT_STATIC;
           int found = -1;
           for (int k = 0; k < n_arb; k++)
             if (S.st.arb[k].a == ia && S.st.arb[k].b == ib) found = k;
@@ -493,7 +522,7 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
               d2 r1 = dsub(m.p1[i], pa), r2 = dsub(m.p2[i], pb);
               C.r1x = r1.x; C.r1y = r1.y; C.r2x = r2.x; C.r2y = r2.y;
               C.nx = m.n.x; C.ny = m.n.y; C.jn = jn; C.jt = jt; C.u = u; C.hash = m.hash[i];
-              C.ba = (uint8_t)(ba < 0 ? 255 : ba); C.bb = (uint8_t)(bb < 0 ? 255 : bb);
+              C.ba = (uint8_t)ba; C.bb = (uint8_t)bb;
               C.arb = (uint8_t)arb_idx; C.slot = (uint8_t)i; C.first = first ? 1 : 0;
               ne.hash[i] = m.hash[i];
             }
@@ -532,15 +561,16 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
 
     /* ---- dependency levels of the contacts (sequential order kept; disjoint contacts share a level) */
     if (lane == 0) {
-      for (int b = 0; b < MG_MAX_BODIES; b++) S.blevel[b] = 0;
+      for (int b = 0; b <= MG_MAX_BODIES; b++) S.blevel[b] = 0;
       int mx = 0;
       for (int c = 0; c < ncon; c++) {
         int ba = S.con[c].ba, bb = S.con[c].bb;
-        int la = (ba < MG_MAX_BODIES && is_dyn(S, ba)) ? S.blevel[ba] : 0;
-        int lb = (bb < MG_MAX_BODIES && is_dyn(S, bb)) ? S.blevel[bb] : 0;
+        /* bodies without inverse mass (static, kinematic) are never written: no dependency through them */
+        int la = (S.MI[ba].x != 0.0 || S.MI[ba].y != 0.0) ? S.blevel[ba] : 0;
+        int lb = (S.MI[bb].x != 0.0 || S.MI[bb].y != 0.0) ? S.blevel[bb] : 0;
         int lv = (la > lb ? la : lb) + 1;
-        if (ba < MG_MAX_BODIES) S.blevel[ba] = (uint8_t)lv;
-        if (bb < MG_MAX_BODIES) S.blevel[bb] = (uint8_t)lv;
+        S.blevel[ba] = (uint8_t)lv;
+        S.blevel[bb] = (uint8_t)lv;
         S.clevel[c] = (uint8_t)lv;
         if (lv > mx) mx = lv;
       }
@@ -552,22 +582,22 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
     /* ---- contact prestep: everything a contact needs for the solve lives in this lane's registers */
     double c_r1x = 0, c_r1y = 0, c_r2x = 0, c_r2y = 0, c_nx = 0, c_ny = 0, c_nMass = 0, c_tMass = 0, c_bias = 0;
     double c_jn = 0, c_jt = 0, c_jb = 0, c_u = 0, c_ma = 0, c_ia = 0, c_mb = 0, c_ib = 0;
-    int c_ba = -1, c_bb = -1, c_level = 0, c_first = 1;
+    int c_ba = SLOT_STATIC, c_bb = SLOT_STATIC, c_level = 0, c_first = 1;
     if (lane < ncon) {
       const ConSmem& C = S.con[lane];
       c_r1x = C.r1x; c_r1y = C.r1y; c_r2x = C.r2x; c_r2y = C.r2y; c_nx = C.nx; c_ny = C.ny;
       c_jn = C.jn; c_jt = C.jt; c_u = C.u; c_first = C.first;
-      c_ba = C.ba == 255 ? -1 : C.ba; c_bb = C.bb == 255 ? -1 : C.bb;
+      c_ba = C.ba; c_bb = C.bb;
       c_level = S.clevel[lane];
-      double2 ma = ld_mi(S, c_ba), mb = ld_mi(S, c_bb);
+      double2 ma = S.MI[c_ba], mb = S.MI[c_bb];
       c_ma = ma.x; c_ia = ma.y; c_mb = mb.x; c_ib = mb.y;
       d2 r1 = D2(c_r1x, c_r1y), r2 = D2(c_r2x, c_r2y), n = D2(c_nx, c_ny), t = dperp(n);
       double rcn1 = dcross(r1, n), rcn2 = dcross(r2, n);
       c_nMass = 1.0 / ((c_ma + c_ia * rcn1 * rcn1) + (c_mb + c_ib * rcn2 * rcn2));
       double rct1 = dcross(r1, t), rct2 = dcross(r2, t);
       c_tMass = 1.0 / ((c_ma + c_ia * rct1 * rct1) + (c_mb + c_ib * rct2 * rct2));
-      d2 pa = (c_ba >= 0) ? D2(S.st.P[c_ba].x, S.st.P[c_ba].y) : D2(0, 0);
-      d2 pb = (c_bb >= 0) ? D2(S.st.P[c_bb].x, S.st.P[c_bb].y) : D2(0, 0);
+      d2 pa = (c_ba < MG_MAX_BODIES) ? D2(S.st.P[c_ba].x, S.st.P[c_ba].y) : D2(0, 0);
+      d2 pb = (c_bb < MG_MAX_BODIES) ? D2(S.st.P[c_bb].x, S.st.P[c_bb].y) : D2(0, 0);
       d2 body_delta = dsub(pb, pa);
       double dist = ddot(dadd(dsub(r2, r1), body_delta), n);
       c_bias = -ds->aux.contact_bias_coef * dminf(0.0, dist + MG_COLLISION_SLOP) / dt;
@@ -601,13 +631,13 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
     for (int it = 0; it < MG_ITERATIONS; ++it) {
       for (int L = 1; L <= max_clevel; L++) {
         if (lane < ncon && c_level == L) {
-          Vel va = ld_vel(S, c_ba), vb = ld_vel(S, c_bb);
-          Vel ba_ = ld_bias(S, c_ba), bb_ = ld_bias(S, c_bb);
+          double4 va = S.V[c_ba], vb = S.V[c_bb];
+          double4 ba_ = S.Bv[c_ba], bb_ = S.Bv[c_bb];
           /* vb1 = a.v_bias + perp(r1)*a.w_bias, etc. */
-          double vb1x = ba_.vx + (-c_r1y) * ba_.w, vb1y = ba_.vy + c_r1x * ba_.w;
-          double vb2x = bb_.vx + (-c_r2y) * bb_.w, vb2y = bb_.vy + c_r2x * bb_.w;
-          double v1x = va.vx + (-c_r1y) * va.w, v1y = va.vy + c_r1x * va.w;
-          double v2x = vb.vx + (-c_r2y) * vb.w, v2y = vb.vy + c_r2x * vb.w;
+          double vb1x = ba_.x + (-c_r1y) * ba_.z, vb1y = ba_.y + c_r1x * ba_.z;
+          double vb2x = bb_.x + (-c_r2y) * bb_.z, vb2y = bb_.y + c_r2x * bb_.z;
+          double v1x = va.x + (-c_r1y) * va.z, v1y = va.y + c_r1x * va.z;
+          double v2x = vb.x + (-c_r2y) * vb.z, v2y = vb.y + c_r2x * vb.z;
           double vrx = v2x - v1x, vry = v2y - v1y;
           double vbn = (vb2x - vb1x) * c_nx + (vb2y - vb1y) * c_ny;
           double vrn = vrx * c_nx + vry * c_ny;
@@ -656,6 +686,10 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
   }
 
   /* ---- stream the record back */
+  if (lane < MG_MAX_BODIES) {
+    S.st.V[lane] = S.V[lane];
+    S.st.Bv[lane] = S.Bv[lane];
+  }
   if (lane == 0) {
     S.st.stamp = stamp;
     S.st.n_arb = n_arb;

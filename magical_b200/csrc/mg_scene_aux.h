@@ -37,6 +37,12 @@ typedef struct {
   uint8_t sched[MG_MAX_LEVELS][32]; /* joint index or 255 */
   uint8_t springs[MG_MAX_JOINTS];   /* spring joints in insertion order (their preStep is sequential) */
   double contact_bias_coef;         /* 1 - pow(collision_bias, dt) */
+  double body_reach[MG_MAX_BODIES]; /* max distance of any point of the body's shapes from its origin */
+  /* per-joint solver constants packed for 128-bit loads: ma, ia, mb, ib (inverse mass / moment of the two
+   * bodies, 0 for static and kinematic ones), c0 (pivot k diagonal or iSum), c1 (max_force*dt),
+   * c2 (spring w_coef | gear ratio), c3 (gear 1/ratio) */
+  double jc[MG_MAX_JOINTS][8];
+  uint8_t jkind[MG_MAX_JOINTS], ja[MG_MAX_JOINTS], jb[MG_MAX_JOINTS]; /* body slots; 16 = the static body */
   int32_t ok;                       /* 0 if the scene uses a feature the kernels do not implement */
   int32_t pad_;
 } mg_scene_aux_t;
@@ -153,6 +159,29 @@ static inline const char* mg_build_scene_aux(const mg_scene_t* s, mg_scene_aux_t
     if (per_level[lvl - 1] >= 32) return "too many joints in one level";
     aux->sched[lvl - 1][per_level[lvl - 1]++] = (uint8_t)j;
     if (lvl > aux->n_levels) aux->n_levels = lvl;
+  }
+  for (int j = 0; j < s->n_joints; j++) {
+    const mg_joint_t* jt = &s->joints[j];
+    aux->jkind[j] = (uint8_t)jt->kind;
+    aux->ja[j] = (uint8_t)(jt->a < 0 ? MG_MAX_BODIES : jt->a);
+    aux->jb[j] = (uint8_t)jt->b;
+    aux->jc[j][0] = jt->a < 0 ? 0.0 : s->bodies[jt->a].m_inv;
+    aux->jc[j][1] = jt->a < 0 ? 0.0 : s->bodies[jt->a].i_inv;
+    aux->jc[j][2] = s->bodies[jt->b].m_inv;
+    aux->jc[j][3] = s->bodies[jt->b].i_inv;
+    aux->jc[j][4] = aux->j_isum[j];
+    aux->jc[j][5] = aux->j_jmax[j];
+    aux->jc[j][6] = jt->kind == MG_JOINT_ROTARY_SPRING ? aux->j_wcoef[j] : (jt->kind == MG_JOINT_GEAR ? jt->p1 : 0.0);
+    aux->jc[j][7] = jt->kind == MG_JOINT_GEAR ? 1.0 / jt->p1 : 0.0;
+  }
+  for (int i = 0; i < s->n_shapes; i++) {
+    const mg_shape_t* sh = &s->shapes[i];
+    if (sh->body < 0) continue;
+    for (int k = 0; k < sh->nvert; k++) {
+      double d = sqrt(s->cverts[sh->vert0 + k][0] * s->cverts[sh->vert0 + k][0] +
+                      s->cverts[sh->vert0 + k][1] * s->cverts[sh->vert0 + k][1]) + sh->radius;
+      if (d > aux->body_reach[sh->body]) aux->body_reach[sh->body] = d;
+    }
   }
   for (int g = 0; g < s->n_cgroups; g++) {
     if (s->cgroups[g].shape0 + s->cgroups[g].nshape > s->n_shapes) return "cgroup shape range";

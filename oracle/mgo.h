@@ -79,6 +79,7 @@ typedef struct mgo_env {
   int episode_steps;
   int overflow;
   int det_sincos;
+  long stat_substeps, stat_bb_pass, stat_circle_pass, stat_hits, stat_contacts; /* instrumentation */
   int32_t* pair_perm; /* optional permutation of the canonical pair order (sensitivity study) */
   /* Robot.set_action state */
   double rel_turn_angle, target_speed, target_finger_angle;
@@ -102,6 +103,7 @@ void mgo_get_state(const mgo_env* e, mg_state_t* out);
 void mgo_set_pose(mgo_env* e, int body, double x, double y, double angle);
 void mgo_collide(const mgo_env* e, int ia, int ib, int* out_a, int* out_b, v2* n, int* count, v2 p1[2], v2 p2[2],
                  unsigned hash[2]);
+void mgo_get_stats(const mgo_env* e, long out[5]);
 double mgo_score(mgo_env* e);
 double mgo_debug_reward(mgo_env* e);
 int mgo_block_in_goal(mgo_env* e, int block, int goal);

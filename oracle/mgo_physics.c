@@ -473,11 +473,27 @@ static void collide_shapes(mgo_env* e, int sa, int sb) {
   if (!bb_intersects(A->bb, B->bb)) return;
   if (A->body == B->body) return;
   if (A->group != 0 && A->group == B->group) return;
+  e->stat_bb_pass++;
+  {
+    /* instrumentation only: would a bounding-circle test have culled this pair? */
+    double ca[2] = {0.5 * (A->bb[0] + A->bb[2]), 0.5 * (A->bb[1] + A->bb[3])};
+    double cb[2] = {0.5 * (B->bb[0] + B->bb[2]), 0.5 * (B->bb[1] + B->bb[3])};
+    double ra = 0, rb = 0;
+    for (int k = 0; k < A->nvert; k++) { double d = hypot(A->tv[k].x - ca[0], A->tv[k].y - ca[1]); if (d > ra) ra = d; }
+    for (int k = 0; k < B->nvert; k++) { double d = hypot(B->tv[k].x - cb[0], B->tv[k].y - cb[1]); if (d > rb) rb = d; }
+    if (A->kind != MG_SHAPE_SEGMENT && B->kind != MG_SHAPE_SEGMENT) {
+      if (hypot(ca[0] - cb[0], ca[1] - cb[1]) <= ra + rb + A->radius + B->radius) e->stat_circle_pass++;
+    } else {
+      e->stat_circle_pass++;
+    }
+  }
   int ia, ib, count;
   v2 n, p1[2], p2[2];
   unsigned hash[2];
   mgo_collide(e, sa, sb, &ia, &ib, &n, &count, p1, p2, hash);
   if (count == 0) return;
+  e->stat_hits++;
+  e->stat_contacts += count;
   mgo_arbiter* arb = arbiter_find(e, ia, ib, 1);
   if (!arb) return;
   /* cpArbiterUpdate */
@@ -717,7 +733,13 @@ static void joint_apply_impulse(mgo_env* e, mgo_joint* j, double dt) {
 }
 
 /* ------------------------------------------------------------ space step */
+void mgo_get_stats(const mgo_env* e, long out[5]) {
+  out[0] = e->stat_substeps; out[1] = e->stat_bb_pass; out[2] = e->stat_circle_pass; out[3] = e->stat_hits;
+  out[4] = e->stat_contacts;
+}
+
 void mgo_space_step(mgo_env* e, double dt) {
+  e->stat_substeps++;
   e->stamp++;
   double prev_dt = e->curr_dt;
   e->curr_dt = dt;
