@@ -52,6 +52,7 @@ struct RPrim {
   int16_t col0, col1;   /* sample columns of the bounding box (inclusive) */
   int32_t span0;        /* offset of this primitive's rows in the span table */
   float sgn;            /* winding sign of the window-space polygon */
+  float ymin, ymax;     /* vertical extent of the window-space vertices */
 };
 
 struct Camera {
@@ -118,7 +119,7 @@ __device__ __forceinline__ float2 prim_vertex(const EnvState& st, const mg_scene
 
 struct ViewSmem {
   RPrim* prims;     /* [RMAXP] */
-  float4* edges;    /* [ecap + 2*RMAXP] */
+  float4* edges;    /* [ecap + 2*RMAXP]  (A, B, C, ymin of the edge) */
   float2* verts;    /* [ecap] */
   short2* spans;    /* [scap] (lo, hi) per (primitive, row) */
   uint32_t* tiles;  /* [RGRID*RGRID*RWORDS] */
@@ -152,15 +153,25 @@ __device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restr
   const float y = (float)j + 0.5f;
   if (R.ne > 0) {
     const int e1 = R.e0 + R.ne;
+    /* Many-sided polygons: an edge can only bound this row if the row lies within one sample of the
+     * edge's own y-extent (the polygon is convex; edges further away are satisfied with a margin of
+     * >= 0.05 px for the 10/20/100-gons drawn here, far above fp32 rounding).  Rows beyond the
+     * polygon's vertices are empty. */
+    const bool filter = R.ne > 8;
+    if (filter && (y > R.ymax + 0.01f || y < R.ymin - 0.01f)) return make_short2((short)lo, (short)(lo - 1));
     for (int e = R.e0; e < e1 && lo <= hi; e++) {
       float4 E = edges[e];
       const float A = E.x;
+      if (filter) {
+        /* |A| = |a.y - b.y| is the edge's y-extent, E.w its lower end */
+        if (y < E.w - 1.0f || y > E.w + fabsf(A) + 1.0f) continue;
+      }
       const float t = fmaf(E.y, y, E.z);
       auto ok = [&](int i) { return fmaf(A, (float)i + 0.5f, t) >= 0.0f; };
       if (A > 0.0f) {
-        lo = first_true(-t / A - 0.5f, lo, hi, ok);
+        lo = first_true(__fdividef(-t, A) - 0.5f, lo, hi, ok);
       } else if (A < 0.0f) {
-        hi = last_true(-t / A - 0.5f, lo, hi, ok);
+        hi = last_true(__fdividef(-t, A) - 0.5f, lo, hi, ok);
       } else if (!(t >= 0.0f)) {
         hi = lo - 1;
       }
@@ -258,7 +269,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
           RPrim& R = vs.prims[rp0 + k];
           const int slot = ecap + 2 * (rp0 + k);
           R.rgb = rgb | ((uint32_t)(pr.stipple != 0xFFFF) << 24);
-          R.ne = 0; R.e0 = (uint16_t)slot; R.sgn = 1.0f; R.span0 = 0;
+          R.ne = 0; R.e0 = (uint16_t)slot; R.sgn = 1.0f; R.span0 = 0; R.ymin = 0.0f; R.ymax = 0.0f;
           if (L > 0.0f) {
             float ux = dx / L, uy = dy / L;
             float minx = fminf(a.x, b.x) - hw - 1.0f, maxx = fmaxf(a.x, b.x) + hw + 1.0f;
@@ -290,6 +301,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
       int j0 = (int)fmaxf(0.0f, floorf(b - 1.0f)), j1 = (int)fminf((float)(res_full - 1), ceilf(t + 1.0f));
       R.rgb = rgb;
       R.sgn = (area2 >= 0.0f) ? 1.0f : -1.0f;
+      R.ymin = b; R.ymax = t;
       R.e0 = (uint16_t)v0; R.ne = (uint16_t)n; R.span0 = 0;
       R.col0 = (int16_t)i0; R.col1 = (int16_t)i1; R.row0 = (int16_t)j0;
       R.nrows = (int16_t)((j1 >= j0 && i1 >= i0) ? (j1 - j0 + 1) : 0);
@@ -319,7 +331,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     float sgn = vs.prims[rp0].sgn;
     float A = a.y - b.y, B = b.x - a.x;
     float C = -fmaf(A, a.x, B * a.y);
-    vs.edges[v] = make_float4(A * sgn, B * sgn, C * sgn, 0.0f);
+    vs.edges[v] = make_float4(A * sgn, B * sgn, C * sgn, fminf(a.y, b.y));
   }
   __syncthreads();
   /* E: spans, one work item per (primitive, row) */
@@ -362,77 +374,102 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   __syncthreads();
 }
 
-/* colour of output pixel (X, Yg): front-to-back walk over the tile's primitives */
+/* round-half-even mean of SSxSS samples (cv2 INTER_AREA: saturate_cast<uchar>(sum / 16.f)) */
 template <int SS>
-__device__ __forceinline__ uint32_t shade(const ViewSmem& vs, int X, int Yg, int tile, float px_scale) {
-  constexpr uint32_t FULLM = (SS == 4) ? 0xFFFFu : 1u;
-  constexpr uint32_t ROWM = (1u << SS) - 1u;
-  uint32_t unresolved = FULLM;
-  uint32_t sr = 0, sg = 0, sb = 0;
-  const uint32_t* tm = vs.tiles + tile * RWORDS;
-  const int cover = vs.cover[tile];
-  const int x0 = X * SS, y0 = Yg * SS;
-  for (int w = RWORDS - 1; w >= 0 && unresolved; w--) {
-    uint32_t bits = tm[w];
-    if (cover >= 0 && (cover >> 5) == w) bits &= ~((1u << (cover & 31)) - 1u); /* nothing shows through it */
-    while (bits && unresolved) {
-      int b = 31 - __clz(bits);
-      bits &= ~(1u << b);
-      const int p = w * 32 + b;
-      const RPrim& R = vs.prims[p];
-      uint32_t m;
-      if (p == cover) {
-        m = unresolved;
-      } else {
-        m = 0u;
-#pragma unroll
-        for (int r = 0; r < SS; r++) {
-          int row = y0 + r - R.row0;
-          if (row >= 0 && row < R.nrows) {
-            short2 s = vs.spans[R.span0 + row];
-            int l = max((int)s.x - x0, 0), h = min((int)s.y - x0, SS - 1);
-            if (l <= h) m |= ((ROWM >> (SS - 1 - (h - l))) << l) << (SS * r);
-          }
-        }
-        m &= unresolved;
-        if (m && (R.rgb >> 24)) {
-          /* stippled line: GL stipple bit from the distance along the loop, per covered sample */
-          float4 pp = vs.edges[R.e0], q = vs.edges[R.e0 + 1];
-          uint32_t stipple = __float_as_uint(q.w);
-          uint32_t keep = 0u, mm = m;
-          while (mm) {
-            int s = __ffs(mm) - 1;
-            mm &= mm - 1;
-            float x = ((float)(x0 + (s % SS))) + 0.5f, y = ((float)(y0 + (s / SS))) + 0.5f;
-            float along = fmaf(x - pp.x, pp.z, (y - pp.y) * pp.w);
-            int bit = ((int)floorf((q.y + along) / px_scale)) & 15;
-            keep |= ((stipple >> bit) & 1u) << s;
-          }
-          m = keep;
-        }
-      }
-      if (m) {
-        uint32_t cnt = __popc(m);
-        sr += cnt * (R.rgb & 0xFF);
-        sg += cnt * ((R.rgb >> 8) & 0xFF);
-        sb += cnt * ((R.rgb >> 16) & 0xFF);
-        unresolved &= ~m;
-      }
-    }
-    if (cover >= 0 && (cover >> 5) == w) break;
-  }
-  if (unresolved) {
-    uint32_t cnt = __popc(unresolved);
-    sr += cnt * BG_R; sg += cnt * BG_G; sb += cnt * BG_B;
-  }
+__device__ __forceinline__ uint32_t finish_colour(uint32_t sr, uint32_t sg, uint32_t sb) {
   if (SS == 4) {
-    /* cv2 INTER_AREA: saturate_cast<uchar>(sum / 16.f) = round half to even */
     uint32_t q, rem;
     q = sr >> 4; rem = sr & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sr = q;
     q = sg >> 4; rem = sg & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sg = q;
     q = sb >> 4; rem = sb & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sb = q;
   }
   return sr | (sg << 8) | (sb << 16);
+}
+
+/* Colours of the 4 output pixels (X0..X0+3, Yg): front-to-back walk over the tile's primitives.
+ * `words` has a bit per non-empty word of the tile's primitive mask (above the covering primitive). */
+template <int SS>
+__device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int tile, int cover, uint32_t words,
+                                       float px_scale, uint32_t out[4]) {
+  constexpr uint32_t FULLM = (SS == 4) ? 0xFFFFu : 1u;
+  uint32_t unres[4] = {FULLM, FULLM, FULLM, FULLM};
+  uint32_t sr[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  const uint32_t* tm = vs.tiles + tile * RWORDS;
+  const int x0 = X0 * SS, y0 = Yg * SS;
+  uint32_t any = FULLM;
+  while (words && any) {
+    const int w = 31 - __clz(words);
+    words &= ~(1u << w);
+    uint32_t bits = tm[w];
+    if (cover >= 0 && (cover >> 5) == w) bits &= ~((1u << (cover & 31)) - 1u); /* nothing shows through it */
+    while (bits && any) {
+      int b = 31 - __clz(bits);
+      bits &= ~(1u << b);
+      const int p = w * 32 + b;
+      const RPrim& R = vs.prims[p];
+      uint32_t m[4];
+      if (p == cover) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) m[i] = unres[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) m[i] = 0u;
+#pragma unroll
+        for (int r = 0; r < SS; r++) {
+          int row = y0 + r - R.row0;
+          if (row >= 0 && row < R.nrows) {
+            short2 sp = vs.spans[R.span0 + row];
+            /* columns of the 4*SS-sample strip covered by this row */
+            int l = max((int)sp.x - x0, 0), h = min((int)sp.y - x0, 4 * SS - 1);
+            if (l <= h) {
+              uint32_t strip = (0xFFFFFFFFu >> (31 - (h - l))) << l; /* bit c = sample column x0 + c */
+              if (SS == 4) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) m[i] |= ((strip >> (4 * i)) & 0xFu) << (4 * r);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) m[i] |= (strip >> i) & 1u;
+              }
+            }
+          }
+        }
+        const bool stippled = (R.rgb >> 24) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          m[i] &= unres[i];
+          if (stippled && m[i]) {
+            /* stippled line: GL stipple bit from the distance along the loop, per covered sample */
+            float4 pp = vs.edges[R.e0], q = vs.edges[R.e0 + 1];
+            uint32_t stipple = __float_as_uint(q.w);
+            uint32_t keep = 0u, mm = m[i];
+            while (mm) {
+              int s = __ffs(mm) - 1;
+              mm &= mm - 1;
+              float x = ((float)(x0 + SS * i + (s % SS))) + 0.5f, y = ((float)(y0 + (s / SS))) + 0.5f;
+              float along = fmaf(x - pp.x, pp.z, (y - pp.y) * pp.w);
+              int bit = ((int)floorf((q.y + along) / px_scale)) & 15;
+              keep |= ((stipple >> bit) & 1u) << s;
+            }
+            m[i] = keep;
+          }
+        }
+      }
+      const uint32_t cr = R.rgb & 0xFF, cg = (R.rgb >> 8) & 0xFF, cb = (R.rgb >> 16) & 0xFF;
+      any = 0u;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        uint32_t cnt = __popc(m[i]);
+        sr[i] += cnt * cr; sg[i] += cnt * cg; sb[i] += cnt * cb;
+        unres[i] &= ~m[i];
+        any |= unres[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint32_t cnt = __popc(unres[i]);
+    out[i] = finish_colour<SS>(sr[i] + cnt * BG_R, sg[i] + cnt * BG_G, sb[i] + cnt * BG_B);
+  }
 }
 
 /* shift one pixel's 12 stack bytes left by one frame and append colour n (or replicate when fresh) */
@@ -497,15 +534,46 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
 
   for (int tile = hw_id; tile < RGRID * RGRID; tile += n_hw) {
     const int tx = tile % RGRID, ty = tile / RGRID; /* ty counts GL rows (bottom-up) */
+    /* per tile and view: the covering primitive, which mask words hold primitives above it, and whether
+     * the whole tile is one flat colour (nothing above the cover / nothing at all) */
+    int cover[NV];
+    uint32_t words[NV], flat_col[NV];
+    bool flat[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      cover[v] = vsm[v].cover[tile];
+      const uint32_t* tm = vsm[v].tiles + tile * RWORDS;
+      uint32_t wm = 0u, above = 0u;
+      for (int w = 0; w < RWORDS; w++) {
+        uint32_t bits = tm[w];
+        if (cover[v] >= 0) {
+          if ((cover[v] >> 5) > w) bits = 0u;
+          else if ((cover[v] >> 5) == w) bits &= ~((1u << (cover[v] & 31)) - 1u);
+        }
+        if (bits) wm |= 1u << w;
+        uint32_t others = bits;
+        if (cover[v] >= 0 && (cover[v] >> 5) == w) others &= ~(1u << (cover[v] & 31));
+        above |= others;
+      }
+      words[v] = wm;
+      flat[v] = (above == 0u);
+      uint32_t c = (cover[v] >= 0) ? (vsm[v].prims[cover[v]].rgb & 0xFFFFFFu) : (BG_R | (BG_G << 8) | (BG_B << 16));
+      flat_col[v] = c;
+    }
     for (int g = hl; g < gpt; g += 16) {
       const int Yg = ty * T + g / gpr;
       const int X0 = tx * T + (g % gpr) * 4;
       const int Y = res_out - 1 - Yg;       /* output row, 0 = top */
       uint32_t col[NV][4];
 #pragma unroll
-      for (int v = 0; v < NV; v++)
+      for (int v = 0; v < NV; v++) {
+        if (flat[v]) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) col[v][i] = shade<SS>(vsm[v], X0 + i, Yg, tile, px_scale);
+          for (int i = 0; i < 4; i++) col[v][i] = flat_col[v];
+        } else {
+          shade4<SS>(vsm[v], X0, Yg, tile, cover[v], words[v], px_scale, col[v]);
+        }
+      }
 
       if (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK) {
         /* [B, R, R, 12] (LoResStack: [2, B, R, R, 12]): 4 pixels = 48 bytes = 3 x uint4 */

@@ -4,6 +4,7 @@ instruction counts and stall samples.  usage: ncu_lines.py <rep> <cubin> <kernel
 import csv, re, subprocess, sys, collections
 rep, cubin, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+SORTK = 1 if (len(sys.argv) > 5 and sys.argv[5] == "inst") else 0
 sass = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(sass.splitlines()))
 hdr = rows[1] if rows[0][0] == 'Kernel Name' else rows[0]
@@ -35,5 +36,5 @@ def src(ln):
         try: srcs[f] = open('/root/repo/magical_b200/csrc/' + f).read().splitlines()
         except Exception: srcs[f] = []
     return srcs[f][n_ - 1].strip()[:80] if 0 < n_ <= len(srcs[f]) else ''
-for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][SORTK])[:top]:
     print(f'{a[0]/ts*100:5.1f}% smp {a[1]/ti*100:5.1f}% inst thr={a[2]/max(a[1],1):4.1f}  {ln}  {src(ln)}')
