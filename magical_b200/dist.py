@@ -40,10 +40,16 @@ def all_gather_shards(local, sizes, group=None):
                           dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
-    bufs = [torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype,
-                        device=local.device) for n in sizes]
-    dist.all_gather(bufs, local.contiguous(), group=group)
-    return torch.cat(bufs, dim=0)
+    # uneven shards: pad to the largest shard, gather, trim
+    nmax = max(sizes)
+    padded = torch.zeros((nmax,) + tuple(local.shape[1:]), dtype=local.dtype,
+                         device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty((world * nmax,) + tuple(local.shape[1:]),
+                      dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    out = out.view((world, nmax) + tuple(local.shape[1:]))
+    return torch.cat([out[r, :sizes[r]] for r in range(world)], dim=0)
 
 
 class ShardedVecEnv:
