@@ -22,7 +22,7 @@
 #include "mg_sincos.h"
 
 cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
-                              cudaStream_t stream);
+                              int lanes_per_env, cudaStream_t stream);
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int batch, int auto_reset, int mode,
                              float* reward, uint8_t* done, float* score, cudaStream_t stream);
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
@@ -44,6 +44,7 @@ struct mg_handle {
   int res_out;
   int ecap;
   int scap;             /* span-table rows the rasteriser reserves per view */
+  int lanes_per_env;    /* 16: two environments share a warp in K1; 32: one warp per environment */
   int64_t launches;
 };
 
@@ -146,6 +147,15 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   }
   ecap = (ecap + 63) / 64 * 64;
   scap = (scap + 63) / 64 * 64;
+  /* K1 serves one environment with 16 lanes when every schedule level fits (it does for all registered
+   * tasks), which doubles the environments in flight per SM; MG_LANES_PER_ENV=32 forces a full warp */
+  int lanes = 16;
+  for (int i = 0; i < cfg->n_scenes; i++)
+    if (host[i].aux.max_per_level > 16) lanes = 32;
+  if (const char* ev = getenv("MG_LANES_PER_ENV")) {
+    int v = atoi(ev);
+    if (v == 32 || (v == 16 && lanes == 16)) lanes = v;
+  }
   if (mg_raster_smem_bytes(cfg->obs_mode, ecap, scap) > 200 * 1024)
     return fail(MG_E_INVALID, "mg_create: scene has too many draw edges for the rasteriser's shared memory%s", "");
 
@@ -157,6 +167,7 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   h->res_out = res_out;
   h->ecap = ecap;
   h->scap = scap;
+  h->lanes_per_env = lanes;
   h->obs_bytes = obs_bytes_for(cfg, res_out);
   cudaError_t e;
   if ((e = cudaMalloc(&h->d_states, sizeof(EnvState) * (size_t)cfg->batch)) != cudaSuccess ||
@@ -251,7 +262,7 @@ int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* sce
 static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
   if (!actions_dev) return fail(MG_E_INVALID, "mg_step: null actions%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->stream));
+  CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->stream));
   CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, h->cfg.auto_reset, 0, reward_dev, done_dev,
                             score_dev, h->stream));
   h->launches += 2;
@@ -308,14 +319,13 @@ int mg_get_state(mg_handle* h, int32_t env, mg_state_t* out) {
   }
   for (int j = 0; j < ds->s.n_joints; j++) { out->joint_acc[j][0] = st.jacc[j].x; out->joint_acc[j][1] = st.jacc[j].y; }
   int nc = 0;
-  for (int k = 0; k < st.n_arb && k < MG_NARB; k++) {
-    if (st.arb[k].stamp != st.stamp) continue; /* only arbiters that collided in the last sub-step */
-    for (int c = 0; c < st.arb[k].count && nc < 32; c++, nc++) {
-      out->contact_shapes[nc][0] = st.arb[k].a;
-      out->contact_shapes[nc][1] = st.arb[k].b;
-      out->contact_jn[nc] = st.arb[k].jn[c];
-      out->contact_jt[nc] = st.arb[k].jt[c];
-    }
+  for (int k = 0; k < st.n_cache && k < MG_NCACHE && nc < 32; k++) {
+    if (st.cache[k].stamp != st.stamp) continue; /* only contacts of the last sub-step */
+    out->contact_shapes[nc][0] = st.cache[k].a;
+    out->contact_shapes[nc][1] = st.cache[k].b;
+    out->contact_jn[nc] = st.cache[k].jn;
+    out->contact_jt[nc] = st.cache[k].jt;
+    nc++;
   }
   out->n_contacts = nc;
   free(ds);

@@ -11,31 +11,34 @@
 #include "../../include/magical_b200.h"
 #include "mg_scene_aux.h"
 
-#define MG_NARB 24   /* cached arbiters (colliding shape pairs incl. those seen in the last 3 sub-steps) */
-#define MG_NCON 24   /* solver contacts per sub-step */
+#define MG_NCACHE 24 /* cached contacts: this sub-step's + those of pairs that collided in the last 3 sub-steps */
+#define MG_NCON 24   /* solver contacts per sub-step (16 when two environments share a warp) */
 #define MG_NCAND 64  /* narrowphase candidates per sub-step */
 #define MG_PERSISTENCE 3
+#define MG_MAX_PINS 4
 
-/* One cached arbiter = one colliding shape pair with its (<=2) contact accumulators. */
-struct __align__(16) ArbEntry {
+/* One cached contact: Chipmunk keeps jnAcc/jtAcc per contact hash inside the shape pair's arbiter for
+ * `collisionPersistence` steps; a pair's entries all carry the stamp of its last collision. */
+struct __align__(16) CEntry {
   uint8_t a, b;      /* shape indices, type-ordered as Chipmunk's cpCollide orders them */
-  uint8_t count;     /* contacts */
+  uint8_t used;      /* scratch: matched by a collision of the current sub-step */
   uint8_t pad_;
-  int32_t stamp;     /* sub-step stamp of the last collision */
-  uint32_t hash[2];  /* contact feature ids */
-  double jn[2], jt[2];
+  uint32_t hash;     /* contact feature id */
+  int32_t stamp;     /* sub-step stamp of the pair's last collision */
+  int32_t pad2_;
+  double jn, jt;
 };
 
-/* Per-environment simulator state in HBM: one contiguous, 16-byte-aligned record that a
- * warp streams in and out with 128-bit loads (7 per lane). */
+/* Per-environment simulator state in HBM: one contiguous, 16-byte-aligned record that a warp (or
+ * half-warp) streams in and out with 128-bit loads. */
 struct __align__(16) EnvState {
-  int32_t scene, episode_steps, stamp, n_arb, overflow, fresh, last_contacts, pad_;
+  int32_t scene, episode_steps, stamp, n_cache, overflow, fresh, last_contacts, pad_;
   double4 V[MG_MAX_BODIES];  /* vx, vy, w, - */
   double4 Bv[MG_MAX_BODIES]; /* bias velocities vbx, vby, wb, - (consumed by the next position update) */
   double4 P[MG_MAX_BODIES];  /* px, py, angle, - */
   double2 R[MG_MAX_BODIES];  /* cos, sin of angle */
   double2 jacc[MG_MAX_JOINTS];
-  ArbEntry arb[MG_NARB];
+  CEntry cache[MG_NCACHE];
 };
 
 struct DeviceScene {

@@ -212,7 +212,7 @@ __device__ static void reset_state(EnvState& st, const DeviceScene* ds, int scen
   st.scene = scene;
   st.episode_steps = 0;
   st.stamp = 0;
-  st.n_arb = 0;
+  st.n_cache = 0;
   st.overflow = 0;
   st.fresh = 1;
   st.last_contacts = 0;
@@ -274,11 +274,10 @@ __global__ void k_reset(EnvState* __restrict__ states, const DeviceScene* __rest
   EnvState& st = states[env];
   int scene = scene_ids ? scene_ids[i] : (first_time ? 0 : st.scene);
   reset_state(st, scenes + scene, scene);
-  for (int k = 0; k < MG_NARB; k++) {
-    ArbEntry e;
-    e.a = e.b = e.count = e.pad_ = 0; e.stamp = -100; e.hash[0] = e.hash[1] = 0;
-    e.jn[0] = e.jn[1] = e.jt[0] = e.jt[1] = 0.0;
-    st.arb[k] = e;
+  for (int k = 0; k < MG_NCACHE; k++) {
+    CEntry e;
+    e.a = e.b = e.used = e.pad_ = 0; e.hash = 0; e.stamp = -100; e.pad2_ = 0; e.jn = e.jt = 0.0;
+    st.cache[k] = e;
   }
 }
 

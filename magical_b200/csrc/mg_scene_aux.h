@@ -43,6 +43,9 @@ typedef struct {
    * c2 (spring w_coef | gear ratio), c3 (gear 1/ratio) */
   double jc[MG_MAX_JOINTS][8];
   uint8_t jkind[MG_MAX_JOINTS], ja[MG_MAX_JOINTS], jb[MG_MAX_JOINTS]; /* body slots; 16 = the static body */
+  uint8_t jpin[MG_MAX_JOINTS];  /* pin joints: slot of their per-sub-step frame (r1, r2, n, nMass, bias) */
+  int32_t max_per_level;        /* widest schedule level (must fit the lanes that serve one environment) */
+  int32_t pad2_;
   int32_t ok;                       /* 0 if the scene uses a feature the kernels do not implement */
   int32_t pad_;
 } mg_scene_aux_t;
@@ -160,8 +163,15 @@ static inline const char* mg_build_scene_aux(const mg_scene_t* s, mg_scene_aux_t
     aux->sched[lvl - 1][per_level[lvl - 1]++] = (uint8_t)j;
     if (lvl > aux->n_levels) aux->n_levels = lvl;
   }
+  int n_pins = 0;
+  for (int L = 0; L < MG_MAX_LEVELS; L++) if (per_level[L] > aux->max_per_level) aux->max_per_level = per_level[L];
   for (int j = 0; j < s->n_joints; j++) {
     const mg_joint_t* jt = &s->joints[j];
+    aux->jpin[j] = 255;
+    if (jt->kind == MG_JOINT_PIN) {
+      if (n_pins >= 4) return "more than 4 pin joints";
+      aux->jpin[j] = (uint8_t)n_pins++;
+    }
     aux->jkind[j] = (uint8_t)jt->kind;
     aux->ja[j] = (uint8_t)(jt->a < 0 ? MG_MAX_BODIES : jt->a);
     aux->jb[j] = (uint8_t)jt->b;
