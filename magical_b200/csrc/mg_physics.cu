@@ -190,115 +190,112 @@ __device__ __forceinline__ void spring_prestep(EnvSmem& S, const DeviceScene* ds
 }
 
 __device__ __forceinline__ void joint_warm(EnvSmem& S, const DeviceScene* ds, int j) {
-  const int a = ds->aux.ja[j], b = ds->aux.jb[j];
+  const uint32_t hd = __ldg(&ds->aux.jpack[j]);
+  const int kind = hd & 0xFF, a = (hd >> 8) & 0xFF, b = (hd >> 16) & 0xFF;
   const JC c = ld_jc(ds, j);
   double2 acc = S.jacc[j];
-  switch (ds->aux.jkind[j]) {
-    case MG_JOINT_PIVOT:
-      apply_imp(S, a, c.ma, c.ia, -acc.x, -acc.y, 0.0, 0.0);
-      apply_imp(S, b, c.mb, c.ib, acc.x, acc.y, 0.0, 0.0);
-      break;
-    case MG_JOINT_GEAR:
-      S.V[a].z -= acc.x * c.ia * c.c3;
-      S.V[b].z += acc.x * c.ib;
-      break;
-    case MG_JOINT_PIN: {
-      const double* pn = S.pin[ds->aux.jpin[j]];
-      double jx = pn[4] * acc.x, jy = pn[5] * acc.x;
-      apply_imp(S, a, c.ma, c.ia, -jx, -jy, pn[0], pn[1]);
-      apply_imp(S, b, c.mb, c.ib, jx, jy, pn[2], pn[3]);
-    } break;
-    case MG_JOINT_ROTARY_LIMIT:
-    case MG_JOINT_MOTOR:
-      S.V[a].z -= acc.x * c.ia;
-      S.V[b].z += acc.x * c.ib;
-      break;
-    default:
-      break;
+  if (kind == MG_JOINT_PIVOT) {
+    apply_imp(S, a, c.ma, c.ia, -acc.x, -acc.y, 0.0, 0.0);
+    apply_imp(S, b, c.mb, c.ib, acc.x, acc.y, 0.0, 0.0);
+  } else if (kind == MG_JOINT_PIN) {
+    const double* pn = S.pin[hd >> 24];
+    double jx = pn[4] * acc.x, jy = pn[5] * acc.x;
+    apply_imp(S, a, c.ma, c.ia, -jx, -jy, pn[0], pn[1]);
+    apply_imp(S, b, c.mb, c.ib, jx, jy, pn[2], pn[3]);
+  } else if (kind != MG_JOINT_ROTARY_SPRING) {
+    /* gear / rotary limit / motor: a.w -= j*ia(*ratio_inv); b.w += j*ib */
+    double da = acc.x * c.ia;
+    if (kind == MG_JOINT_GEAR) da = da * c.c3;
+    S.V[a].z -= da;
+    S.V[b].z += acc.x * c.ib;
   }
 }
 
+/* One sequential-impulse update of joint j (the constraint's applyImpulse in Chipmunk).  The three purely
+ * angular kinds share one branch-free path: every alternative is evaluated exactly as its reference
+ * formula and selected, so the arithmetic of each kind is unchanged. */
 __device__ __forceinline__ void joint_apply(EnvSmem& S, const DeviceScene* ds, int j) {
-  const int a = ds->aux.ja[j], b = ds->aux.jb[j];
+  const uint32_t hd = __ldg(&ds->aux.jpack[j]);
+  const int kind = hd & 0xFF, a = (hd >> 8) & 0xFF, b = (hd >> 16) & 0xFF;
   const JC c = ld_jc(ds, j);
-  switch (ds->aux.jkind[j]) {
-    case MG_JOINT_PIVOT: {
-      double4 va = S.V[a], vb = S.V[b];
-      double jx = (0.0 - (vb.x - va.x)) * c.c0;
-      double jy = (0.0 - (vb.y - va.y)) * c.c0;
-      double2 old = S.jacc[j];
-      d2 acc = dvclamp(D2(old.x + jx, old.y + jy), c.c1);
-      S.jacc[j] = make_double2(acc.x, acc.y);
-      jx = acc.x - old.x; jy = acc.y - old.y;
-      /* anchors are at the body origins: no angular part (adds exactly zero) */
-      va.x = va.x + (-jx) * c.ma; va.y = va.y + (-jy) * c.ma;
-      vb.x = vb.x + jx * c.mb; vb.y = vb.y + jy * c.mb;
-      S.V[a] = va;
-      S.V[b] = vb;
-    } break;
-    case MG_JOINT_GEAR: {
-      double wr = S.V[b].z * c.c2 - S.V[a].z;
-      double jj = (S.jd[j] - wr) * c.c0;
-      double jOld = S.jacc[j].x;
-      double jNew = dclamp(jOld + jj, -c.c1, c.c1);
-      S.jacc[j].x = jNew;
-      jj = jNew - jOld;
-      S.V[a].z -= jj * c.ia * c.c3;
-      S.V[b].z += jj * c.ib;
-    } break;
-    case MG_JOINT_ROTARY_SPRING: {
-      double wrn = S.V[a].z - S.V[b].z;
-      double w_damp = (S.jd[j] - wrn) * c.c2;
-      S.jd[j] = wrn + w_damp;
-      double j_damp = w_damp * c.c0;
-      S.jacc[j].x += j_damp;
-      S.V[a].z += j_damp * c.ia;
-      S.V[b].z -= j_damp * c.ib;
-    } break;
-    case MG_JOINT_PIN: {
-      const double* pn = S.pin[ds->aux.jpin[j]];
-      d2 r1 = D2(pn[0], pn[1]), r2 = D2(pn[2], pn[3]);
-      d2 n = D2(pn[4], pn[5]);
-      double4 va = S.V[a], vb = S.V[b];
-      d2 v1 = dadd(D2(va.x, va.y), dmul(dperp(r1), va.z));
-      d2 v2 = dadd(D2(vb.x, vb.y), dmul(dperp(r2), vb.z));
-      double vrn = ddot(dsub(v2, v1), n);
-      double jn = (pn[7] - vrn) * pn[6];
-      double jnOld = S.jacc[j].x;
-      double jnNew = dclamp(jnOld + jn, -c.c1, c.c1);
-      S.jacc[j].x = jnNew;
-      jn = jnNew - jnOld;
-      double jx = n.x * jn, jy = n.y * jn;
-      va.x = va.x + (-jx) * c.ma; va.y = va.y + (-jy) * c.ma;
-      va.z += c.ia * (r1.x * (-jy) - r1.y * (-jx));
-      vb.x = vb.x + jx * c.mb; vb.y = vb.y + jy * c.mb;
-      vb.z += c.ib * (r2.x * jy - r2.y * jx);
-      S.V[a] = va;
-      S.V[b] = vb;
-    } break;
-    case MG_JOINT_ROTARY_LIMIT: {
-      double bias = S.jd[j];
-      if (!bias) return;
-      double wr = S.V[b].z - S.V[a].z;
-      double jj = -(bias + wr) * c.c0;
-      double jOld = S.jacc[j].x;
-      double jNew = (bias < 0.0) ? dclamp(jOld + jj, 0.0, c.c1) : dclamp(jOld + jj, -c.c1, 0.0);
-      S.jacc[j].x = jNew;
-      jj = jNew - jOld;
-      S.V[a].z -= jj * c.ia;
-      S.V[b].z += jj * c.ib;
-    } break;
-    case MG_JOINT_MOTOR: {
-      double wr = S.V[b].z - S.V[a].z + S.jd[j];
-      double jj = -wr * c.c0;
-      double jOld = S.jacc[j].x;
-      double jNew = dclamp(jOld + jj, -c.c1, c.c1);
-      S.jacc[j].x = jNew;
-      jj = jNew - jOld;
-      S.V[a].z -= jj * c.ia;
-      S.V[b].z += jj * c.ib;
-    } break;
+  if (kind == MG_JOINT_GEAR || kind == MG_JOINT_ROTARY_LIMIT || kind == MG_JOINT_MOTOR) {
+    const bool gear = kind == MG_JOINT_GEAR, limit = kind == MG_JOINT_ROTARY_LIMIT;
+    const double x = S.jd[j]; /* gear: bias; limit: bias; motor: rate */
+    if (limit && !x) return;  /* joint not at a limit */
+    const double wa = S.V[a].z, wb = S.V[b].z;
+    double wr = gear ? (wb * c.c2 - wa) : (wb - wa);
+    if (!gear && !limit) wr = wr + x;                 /* motor: b.w - a.w + rate */
+    double jj = gear ? (x - wr) * c.c0 : (limit ? -(x + wr) * c.c0 : -wr * c.c0);
+    const double lo = (limit && x < 0.0) ? 0.0 : -c.c1;
+    const double hi = (limit && !(x < 0.0)) ? 0.0 : c.c1;
+    const double jOld = S.jacc[j].x;
+    const double jNew = dclamp(jOld + jj, lo, hi);
+    S.jacc[j].x = jNew;
+    jj = jNew - jOld;
+    double da = jj * c.ia;
+    if (gear) da = da * c.c3;
+    S.V[a].z = wa - da;
+    S.V[b].z = wb + jj * c.ib;
+  } else if (kind == MG_JOINT_PIVOT) {
+    double4 va = S.V[a], vb = S.V[b];
+    double jx = (0.0 - (vb.x - va.x)) * c.c0;
+    double jy = (0.0 - (vb.y - va.y)) * c.c0;
+    double2 old = S.jacc[j];
+    d2 acc = dvclamp(D2(old.x + jx, old.y + jy), c.c1);
+    S.jacc[j] = make_double2(acc.x, acc.y);
+    jx = acc.x - old.x; jy = acc.y - old.y;
+    /* anchors are at the body origins: no angular part (adds exactly zero) */
+    va.x = va.x + (-jx) * c.ma; va.y = va.y + (-jy) * c.ma;
+    vb.x = vb.x + jx * c.mb; vb.y = vb.y + jy * c.mb;
+    S.V[a] = va;
+    S.V[b] = vb;
+  } else if (kind == MG_JOINT_ROTARY_SPRING) {
+    double wa = S.V[a].z, wb = S.V[b].z;
+    double wrn = wa - wb;
+    double w_damp = (S.jd[j] - wrn) * c.c2;
+    S.jd[j] = wrn + w_damp;
+    double j_damp = w_damp * c.c0;
+    S.jacc[j].x += j_damp;
+    S.V[a].z = wa + j_damp * c.ia;
+    S.V[b].z = wb - j_damp * c.ib;
+  } else { /* MG_JOINT_PIN */
+    const double* pn = S.pin[hd >> 24];
+    d2 r1 = D2(pn[0], pn[1]), r2 = D2(pn[2], pn[3]);
+    d2 n = D2(pn[4], pn[5]);
+    double4 va = S.V[a], vb = S.V[b];
+    d2 v1 = dadd(D2(va.x, va.y), dmul(dperp(r1), va.z));
+    d2 v2 = dadd(D2(vb.x, vb.y), dmul(dperp(r2), vb.z));
+    double vrn = ddot(dsub(v2, v1), n);
+    double jn = (pn[7] - vrn) * pn[6];
+    double jnOld = S.jacc[j].x;
+    double jnNew = dclamp(jnOld + jn, -c.c1, c.c1);
+    S.jacc[j].x = jnNew;
+    jn = jnNew - jnOld;
+    double jx = n.x * jn, jy = n.y * jn;
+    va.x = va.x + (-jx) * c.ma; va.y = va.y + (-jy) * c.ma;
+    va.z += c.ia * (r1.x * (-jy) - r1.y * (-jx));
+    vb.x = vb.x + jx * c.mb; vb.y = vb.y + jy * c.mb;
+    vb.z += c.ib * (r2.x * jy - r2.y * jx);
+    S.V[a] = va;
+    S.V[b] = vb;
   }
+}
+
+/* Exact narrowphase of one candidate pair.  Deliberately OUT OF LINE: with the separation cache it runs
+ * rarely, and keeping its ~9k instructions out of the solver loop's neighbourhood is what keeps the hot
+ * code inside the 32 KB instruction cache. */
+__device__ __noinline__ void narrow_pair(const EnvSmem* Sp, const DeviceScene* ds, int ia, int ib, Manifold* out) {
+  const EnvSmem& S = *Sp;
+  ShapeView va = make_view(S, ds, ia), vb = make_view(S, ds, ib);
+  double bba[4], bbb[4];
+  sv_bb(va, bba);
+  sv_bb(vb, bbb);
+  Manifold m;
+  m.count = 0;
+  m.margin = -1.0;
+  m.n = D2(0, 0);
+  if (bb_intersects(bba, bbb)) mg_collide(va, vb, bba, bbb, m);
+  *out = m;
 }
 
 /* cooperative 16-byte copy by the G lanes of one environment */
@@ -493,16 +490,10 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
         for (int k = 0; k < n_sep; k++)
           if (S.sep[k].a == ia && S.sep[k].b == ib) { sep_slot = k; skipped = travelled < S.sep[k].limit; }
         if (!skipped) {
-          ShapeView va = make_view(S, ds, ia), vb = make_view(S, ds, ib);
-          double bba[4], bbb[4];
-          sv_bb(va, bba);
-          sv_bb(vb, bbb);
-          if (bb_intersects(bba, bbb)) {
-            mg_collide(va, vb, bba, bbb, m);
-            /* shapes `margin` apart cannot touch until the bodies have travelled that far */
-            if (m.count == 0 && m.margin > 1e-6)
-              sep_limit = __fadd_rd(travelled, __double2float_rd(m.margin * 0.999999 - 1e-9));
-          }
+          narrow_pair(&S, ds, ia, ib, &m);
+          /* shapes `margin` apart cannot touch until the bodies have travelled that far */
+          if (m.count == 0 && m.margin > 1e-6)
+            sep_limit = __fadd_rd(travelled, __double2float_rd(m.margin * 0.999999 - 1e-9));
         }
       }
       {
@@ -624,12 +615,15 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
       }
       GSYNC();
     }
+    /* joints: lane l walks the joints of connected component l in insertion order; components share
+     * no dynamic body, so no barrier is needed until the contacts run again */
     const int n_levels = ds->aux.n_levels;
     for (int L = 0; L < n_levels; L++) {
       int j = ds->aux.sched[L][gl];
-      if (j != 255) joint_warm(S, ds, j);
-      GSYNC();
+      if (j == 255) break;
+      joint_warm(S, ds, j);
     }
+    GSYNC();
 
     /* ---- solver iterations (cpArbiterApplyImpulse for every arbiter, then every joint) */
     for (int it = 0; it < MG_ITERATIONS; ++it) {
@@ -668,9 +662,10 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
       }
       for (int L = 0; L < n_levels; L++) {
         int j = ds->aux.sched[L][gl];
-        if (j != 255) joint_apply(S, ds, j);
-        GSYNC();
+        if (j == 255) break;
+        joint_apply(S, ds, j);
       }
+      GSYNC();
     }
 
     /* ---- rebuild the contact cache: this sub-step's contacts first (canonical order), then the

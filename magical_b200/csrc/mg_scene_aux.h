@@ -31,7 +31,7 @@ typedef struct {
   double j_wcoef[MG_MAX_JOINTS];  /* spring: 1 - exp(-damping*dt/iSum) */
   double j_bcoef[MG_MAX_JOINTS];  /* bias_coef(error_bias, dt) */
   double j_jmax[MG_MAX_JOINTS];   /* max_force * dt */
-  /* schedule: joints of level L run concurrently, one per lane */
+  /* schedule: lane l walks sched[0..n_levels)[l] (its component's joints in insertion order, 255 = none) */
   int32_t n_levels;
   int32_t n_springs;
   uint8_t sched[MG_MAX_LEVELS][32]; /* joint index or 255 */
@@ -44,7 +44,8 @@ typedef struct {
   double jc[MG_MAX_JOINTS][8];
   uint8_t jkind[MG_MAX_JOINTS], ja[MG_MAX_JOINTS], jb[MG_MAX_JOINTS]; /* body slots; 16 = the static body */
   uint8_t jpin[MG_MAX_JOINTS];  /* pin joints: slot of their per-sub-step frame (r1, r2, n, nMass, bias) */
-  int32_t max_per_level;        /* widest schedule level (must fit the lanes that serve one environment) */
+  uint32_t jpack[MG_MAX_JOINTS]; /* kind | a << 8 | b << 16 | pin slot << 24 */
+  int32_t max_per_level;        /* lanes the joint schedule needs (must fit the lanes that serve one environment) */
   int32_t pad2_;
   int32_t ok;                       /* 0 if the scene uses a feature the kernels do not implement */
   int32_t pad_;
@@ -106,8 +107,7 @@ static inline const char* mg_build_scene_aux(const mg_scene_t* s, mg_scene_aux_t
     }
   }
   /* joints */
-  int last_level[MG_MAX_BODIES];
-  for (int i = 0; i < MG_MAX_BODIES; i++) last_level[i] = 0;
+  int jcomp_a[MG_MAX_JOINTS], jcomp_b[MG_MAX_JOINTS];
   int per_level[MG_MAX_LEVELS];
   for (int i = 0; i < MG_MAX_LEVELS; i++) per_level[i] = 0;
   memset(aux->sched, 255, sizeof(aux->sched));
@@ -151,20 +151,43 @@ static inline const char* mg_build_scene_aux(const mg_scene_t* s, mg_scene_aux_t
       default:
         return "unknown joint kind";
     }
-    /* sequential-order-preserving level: one past the latest level of any dynamic body it touches */
-    int lvl = 0;
-    if (jt->a >= 0 && s->bodies[jt->a].kind == MG_BODY_DYNAMIC && last_level[jt->a] > lvl) lvl = last_level[jt->a];
-    if (s->bodies[jt->b].kind == MG_BODY_DYNAMIC && last_level[jt->b] > lvl) lvl = last_level[jt->b];
-    lvl += 1;
-    if (lvl > MG_MAX_LEVELS) return "joint chain too deep";
-    if (jt->a >= 0 && s->bodies[jt->a].kind == MG_BODY_DYNAMIC) last_level[jt->a] = lvl;
-    if (s->bodies[jt->b].kind == MG_BODY_DYNAMIC) last_level[jt->b] = lvl;
-    if (per_level[lvl - 1] >= 32) return "too many joints in one level";
-    aux->sched[lvl - 1][per_level[lvl - 1]++] = (uint8_t)j;
-    if (lvl > aux->n_levels) aux->n_levels = lvl;
+    /* Chains instead of levels: joints are grouped by the connected component (over dynamic
+     * bodies) they belong to; one lane walks a component's joints in insertion order, and components
+     * share no dynamic body, so no barrier is needed between joints. */
+    jcomp_a[j] = (jt->a >= 0 && s->bodies[jt->a].kind == MG_BODY_DYNAMIC) ? jt->a : -1;
+    jcomp_b[j] = (s->bodies[jt->b].kind == MG_BODY_DYNAMIC) ? jt->b : -1;
+  }
+  {
+    int parent[MG_MAX_BODIES];
+    for (int i = 0; i < MG_MAX_BODIES; i++) parent[i] = i;
+    for (int j = 0; j < s->n_joints; j++) {
+      if (jcomp_a[j] >= 0 && jcomp_b[j] >= 0) {
+        int x = jcomp_a[j], y = jcomp_b[j];
+        while (parent[x] != x) x = parent[x];
+        while (parent[y] != y) y = parent[y];
+        if (x != y) parent[y < x ? x : y] = (y < x ? y : x);
+      }
+    }
+    int comp_lane[MG_MAX_BODIES];
+    for (int i = 0; i < MG_MAX_BODIES; i++) comp_lane[i] = -1;
+    int n_lanes = 0;
+    for (int j = 0; j < s->n_joints; j++) {
+      int body = jcomp_b[j] >= 0 ? jcomp_b[j] : jcomp_a[j];
+      if (body < 0) return "joint between two non-dynamic bodies";
+      while (parent[body] != body) body = parent[body];
+      if (comp_lane[body] < 0) {
+        if (n_lanes >= 32) return "too many joint components";
+        comp_lane[body] = n_lanes++;
+      }
+      int lane = comp_lane[body];
+      int pos = per_level[lane]++; /* per_level[] doubles as the chain length per lane */
+      if (pos >= MG_MAX_LEVELS) return "joint chain too deep";
+      aux->sched[pos][lane] = (uint8_t)j;
+      if (pos + 1 > aux->n_levels) aux->n_levels = pos + 1;
+    }
+    aux->max_per_level = n_lanes;
   }
   int n_pins = 0;
-  for (int L = 0; L < MG_MAX_LEVELS; L++) if (per_level[L] > aux->max_per_level) aux->max_per_level = per_level[L];
   for (int j = 0; j < s->n_joints; j++) {
     const mg_joint_t* jt = &s->joints[j];
     aux->jpin[j] = 255;
@@ -175,6 +198,7 @@ static inline const char* mg_build_scene_aux(const mg_scene_t* s, mg_scene_aux_t
     aux->jkind[j] = (uint8_t)jt->kind;
     aux->ja[j] = (uint8_t)(jt->a < 0 ? MG_MAX_BODIES : jt->a);
     aux->jb[j] = (uint8_t)jt->b;
+    aux->jpack[j] = (uint32_t)aux->jkind[j] | ((uint32_t)aux->ja[j] << 8) | ((uint32_t)aux->jb[j] << 16) | ((uint32_t)aux->jpin[j] << 24);
     aux->jc[j][0] = jt->a < 0 ? 0.0 : s->bodies[jt->a].m_inv;
     aux->jc[j][1] = jt->a < 0 ? 0.0 : s->bodies[jt->a].i_inv;
     aux->jc[j][2] = s->bodies[jt->b].m_inv;
