@@ -22,7 +22,7 @@
 #include "mg_sincos.h"
 
 cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
-                              int lanes_per_env, cudaStream_t stream);
+                              int lanes_per_env, int block_threads, cudaStream_t stream);
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int batch, int auto_reset, int mode,
                              float* reward, uint8_t* done, float* score, cudaStream_t stream);
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
@@ -45,6 +45,7 @@ struct mg_handle {
   int ecap;
   int scap;             /* span-table rows the rasteriser reserves per view */
   int lanes_per_env;    /* 16: two environments share a warp in K1; 32: one warp per environment */
+  int block_threads;    /* K1 block size: 512 = one phase-aligned block per SM, 128 = small blocks */
   int64_t launches;
 };
 
@@ -168,6 +169,12 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   h->ecap = ecap;
   h->scap = scap;
   h->lanes_per_env = lanes;
+  /* phase-aligned 512-thread blocks need enough environments to fill the 148 SMs */
+  h->block_threads = (cfg->batch / (512 / lanes) >= 2 * 148) ? 512 : 128;
+  if (const char* ev = getenv("MG_BLOCK_THREADS")) {
+    int v = atoi(ev);
+    if (v == 128 || v == 512) h->block_threads = v;
+  }
   h->obs_bytes = obs_bytes_for(cfg, res_out);
   cudaError_t e;
   if ((e = cudaMalloc(&h->d_states, sizeof(EnvState) * (size_t)cfg->batch)) != cudaSuccess ||
@@ -262,7 +269,7 @@ int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* sce
 static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
   if (!actions_dev) return fail(MG_E_INVALID, "mg_step: null actions%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->stream));
+  CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads, h->stream));
   CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, h->cfg.auto_reset, 0, reward_dev, done_dev,
                             score_dev, h->stream));
   h->launches += 2;

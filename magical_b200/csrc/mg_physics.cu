@@ -30,7 +30,6 @@
 
 #define SLOT_STATIC MG_MAX_BODIES /* velocity slot of the static body: always reads as zero */
 #define MG_NSEP 32
-#define THREADS 128
 
 struct __align__(8) ConSmem {
   double r1x, r1y, r2x, r2y, nx, ny, jn, jt;
@@ -307,9 +306,12 @@ __device__ __forceinline__ void gcopy16(void* dst, const void* src, int nbytes, 
 }
 
 /* ------------------------------------------------------------------ kernel
- * G lanes per environment (32 or 16); THREADS / G environments per block. */
-template <int G>
-__global__ void __launch_bounds__(THREADS, 4)
+ * G lanes per environment (32 or 16); THREADS / G environments per block.  With THREADS = 512 one block
+ * fills an SM and two block barriers per sub-step keep all its environments in the same phase, so the
+ * instruction working set at any moment is one phase (fits the 32 KB I-cache) instead of the whole
+ * 60 KB sub-step body. */
+template <int G, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 512 ? 1 : 4))
 k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, const int32_t* __restrict__ actions,
           int batch) {
   constexpr int NCONG = (G < MG_NCON) ? G : MG_NCON; /* contacts one group of lanes can own */
@@ -321,7 +323,12 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
   const unsigned gmask = gbits << gbase;
   const int slot = threadIdx.x / G;
   const int env = blockIdx.x * (THREADS / G) + slot;
-  if (env >= batch) return; /* group-uniform; only group-wide barriers are used below */
+  constexpr bool PHASED = THREADS == 512;
+  if (env >= batch) { /* group-uniform */
+    if (PHASED)
+      for (int sub = 0; sub < MG_SUBSTEPS; ++sub) { __syncthreads(); __syncthreads(); }
+    return;
+  }
   EnvSmem& S = reinterpret_cast<EnvSmem*>(smem_raw)[slot];
   EnvState* Gs = states + env;
 #define GSYNC() __syncwarp(gmask)
@@ -606,6 +613,8 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
     }
     GSYNC();
 
+    if (PHASED) __syncthreads(); /* everyone enters the solver together */
+
     /* ---- warm start (cpArbiterApplyCachedImpulse, then the joints' applyCachedImpulse; dt_coef = 1) */
     for (int L = 1; L <= max_clevel; L++) {
       if (gl < ncon && c_level == L && !c_first) {
@@ -704,6 +713,7 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
       n_cache = tot;
     }
     GSYNC();
+    if (PHASED) __syncthreads(); /* everyone leaves the solver together */
   }
 
   /* ---- stream the record back */
@@ -722,27 +732,32 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
 #undef GSYNC
 }
 
-size_t mg_physics_smem_bytes(int lanes_per_env) { return sizeof(EnvSmem) * (size_t)(THREADS / lanes_per_env); }
+size_t mg_physics_smem_bytes(int lanes_per_env, int threads) { return sizeof(EnvSmem) * (size_t)(threads / lanes_per_env); }
 
-template <int G>
+template <int G, int THREADS>
 static cudaError_t launch_g(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
                             cudaStream_t stream) {
   static bool configured = false;
-  size_t smem = mg_physics_smem_bytes(G);
+  size_t smem = mg_physics_smem_bytes(G, THREADS);
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_physics<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_physics<G, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_physics<G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(k_physics<G, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int epb = THREADS / G;
-  k_physics<G><<<(batch + epb - 1) / epb, THREADS, smem, stream>>>(states, scenes, actions, batch);
+  k_physics<G, THREADS><<<(batch + epb - 1) / epb, THREADS, smem, stream>>>(states, scenes, actions, batch);
   return cudaGetLastError();
 }
 
 cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
-                              int lanes_per_env, cudaStream_t stream) {
-  if (lanes_per_env == 16) return launch_g<16>(states, scenes, actions, batch, stream);
-  return launch_g<32>(states, scenes, actions, batch, stream);
+                              int lanes_per_env, int block_threads, cudaStream_t stream) {
+  if (lanes_per_env == 16) {
+    if (block_threads == 512) return launch_g<16, 512>(states, scenes, actions, batch, stream);
+    return launch_g<16, 128>(states, scenes, actions, batch, stream);
+  }
+  if (block_threads == 512) return launch_g<32, 512>(states, scenes, actions, batch, stream);
+  return launch_g<32, 128>(states, scenes, actions, batch, stream);
 }
