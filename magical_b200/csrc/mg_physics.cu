@@ -324,9 +324,12 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
   const int slot = threadIdx.x / G;
   const int env = blockIdx.x * (THREADS / G) + slot;
   constexpr bool PHASED = THREADS == 512;
+  /* block barrier that tolerates the two half-warps of a warp arriving at different times
+   * (__syncthreads() is the aligned form and would require the warp to be converged) */
+#define BLOCK_PHASE_SYNC() asm volatile("barrier.sync 0, %0;" ::"r"(THREADS) : "memory")
   if (env >= batch) { /* group-uniform */
     if (PHASED)
-      for (int sub = 0; sub < MG_SUBSTEPS; ++sub) { __syncthreads(); __syncthreads(); }
+      for (int sub = 0; sub < MG_SUBSTEPS; ++sub) { BLOCK_PHASE_SYNC(); BLOCK_PHASE_SYNC(); }
     return;
   }
   EnvSmem& S = reinterpret_cast<EnvSmem*>(smem_raw)[slot];
@@ -613,7 +616,7 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
     }
     GSYNC();
 
-    if (PHASED) __syncthreads(); /* everyone enters the solver together */
+    if (PHASED) BLOCK_PHASE_SYNC(); /* everyone enters the solver together */
 
     /* ---- warm start (cpArbiterApplyCachedImpulse, then the joints' applyCachedImpulse; dt_coef = 1) */
     for (int L = 1; L <= max_clevel; L++) {
@@ -713,7 +716,7 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
       n_cache = tot;
     }
     GSYNC();
-    if (PHASED) __syncthreads(); /* everyone leaves the solver together */
+    if (PHASED) BLOCK_PHASE_SYNC(); /* everyone leaves the solver together */
   }
 
   /* ---- stream the record back */
@@ -730,6 +733,7 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
     Gs->last_contacts = ncon;
   }
 #undef GSYNC
+#undef BLOCK_PHASE_SYNC
 }
 
 size_t mg_physics_smem_bytes(int lanes_per_env, int threads) { return sizeof(EnvSmem) * (size_t)(threads / lanes_per_env); }
