@@ -30,6 +30,9 @@
 
 #define SLOT_STATIC MG_MAX_BODIES /* velocity slot of the static body: always reads as zero */
 #define MG_NSEP 32
+#ifndef MG_PHASES
+#define MG_PHASES 4 /* block barriers per sub-step in the phase-aligned variant */
+#endif
 
 struct __align__(8) ConSmem {
   double r1x, r1y, r2x, r2y, nx, ny, jn, jt;
@@ -329,7 +332,9 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
 #define BLOCK_PHASE_SYNC() asm volatile("barrier.sync 0, %0;" ::"r"(THREADS) : "memory")
   if (env >= batch) { /* group-uniform */
     if (PHASED)
-      for (int sub = 0; sub < MG_SUBSTEPS; ++sub) { BLOCK_PHASE_SYNC(); BLOCK_PHASE_SYNC(); }
+      for (int sub = 0; sub < MG_SUBSTEPS; ++sub) {
+        for (int k = 0; k < MG_PHASES; ++k) BLOCK_PHASE_SYNC();
+      }
     return;
   }
   EnvSmem& S = reinterpret_cast<EnvSmem*>(smem_raw)[slot];
@@ -480,6 +485,7 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
     }
     if (ncand > MG_NCAND) { ncand = MG_NCAND; overflow |= 1; }
     GSYNC(); /* boxes are dead from here on: the union now holds contacts */
+    if (PHASED && MG_PHASES >= 4) BLOCK_PHASE_SYNC();
 
     /* ---- narrowphase + contact cache lookup (cpCollide + cpArbiterUpdate) */
     ncon = 0;
@@ -563,6 +569,7 @@ k_physics(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes,
     }
     GSYNC();
 
+    if (PHASED && MG_PHASES >= 4) BLOCK_PHASE_SYNC();
     /* ---- dependency levels of the contacts (sequential order kept; disjoint contacts share a level) */
     if (gl == 0) {
       for (int b = 0; b <= MG_MAX_BODIES; b++) S.blevel[b] = 0;

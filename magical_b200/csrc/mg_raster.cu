@@ -119,7 +119,8 @@ __device__ __forceinline__ float2 prim_vertex(const EnvState& st, const mg_scene
 
 struct ViewSmem {
   RPrim* prims;     /* [RMAXP] */
-  float4* edges;    /* [ecap + 2*RMAXP]  (A, B, C, ymin of the edge) */
+  float4* edges;    /* [ecap + 2*RMAXP]  (A, B, C, -) ; line segments: 2 float4 behind the pool */
+  float4* eaux;     /* [ecap] per edge: (m, q, ymin, ymax) with boundary x*(y) = m*y + q */
   float2* verts;    /* [ecap] */
   short2* spans;    /* [scap] (lo, hi) per (primitive, row) */
   uint32_t* tiles;  /* [RGRID*RGRID*RWORDS] */
@@ -148,30 +149,30 @@ __device__ __forceinline__ int last_true(float est, int cmin, int cmax, F ok) {
 }
 
 /* exact covered interval of sample row j for primitive R (empty => lo > hi) */
-__device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restrict__ edges, int j) {
+__device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restrict__ edges,
+                                          const float4* __restrict__ eaux, int j) {
   int lo = R.col0, hi = R.col1;
   const float y = (float)j + 0.5f;
   if (R.ne > 0) {
     const int e1 = R.e0 + R.ne;
-    /* Many-sided polygons: an edge can only bound this row if the row lies within one sample of the
-     * edge's own y-extent (the polygon is convex; edges further away are satisfied with a margin of
-     * >= 0.05 px for the 10/20/100-gons drawn here, far above fp32 rounding).  Rows beyond the
+    /* An edge can only bound this row if the row lies within one sample of the edge's own y-extent:
+     * the polygon is convex, so edges further away are satisfied with a margin (>= 0.05 px for the
+     * 100-gons, more for everything else) that is far above fp32 rounding.  Rows beyond the
      * polygon's vertices are empty. */
-    const bool filter = R.ne > 8;
-    if (filter && (y > R.ymax + 0.01f || y < R.ymin - 0.01f)) return make_short2((short)lo, (short)(lo - 1));
+    if (y > R.ymax + 0.01f || y < R.ymin - 0.01f) return make_short2((short)lo, (short)(lo - 1));
     for (int e = R.e0; e < e1 && lo <= hi; e++) {
-      float4 E = edges[e];
+      const float4 X = eaux[e];
+      /* only edges whose own y-extent comes within one sample of this row can bound it */
+      if (y < X.z - 1.0f || y > X.w + 1.0f) continue;
+      const float4 E = edges[e];
       const float A = E.x;
-      if (filter) {
-        /* |A| = |a.y - b.y| is the edge's y-extent, E.w its lower end */
-        if (y < E.w - 1.0f || y > E.w + fabsf(A) + 1.0f) continue;
-      }
       const float t = fmaf(E.y, y, E.z);
       auto ok = [&](int i) { return fmaf(A, (float)i + 0.5f, t) >= 0.0f; };
+      const float est = fmaf(X.x, y, X.y) - 0.5f; /* boundary column estimate, corrected exactly below */
       if (A > 0.0f) {
-        lo = first_true(__fdividef(-t, A) - 0.5f, lo, hi, ok);
+        lo = first_true(est, lo, hi, ok);
       } else if (A < 0.0f) {
-        hi = last_true(__fdividef(-t, A) - 0.5f, lo, hi, ok);
+        hi = last_true(est, lo, hi, ok);
       } else if (!(t >= 0.0f)) {
         hi = lo - 1;
       }
@@ -292,10 +293,20 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
       RPrim& R = vs.prims[rp0];
       float area2 = 0.0f;
       float l = INFINITY, r = -INFINITY, b = INFINITY, t = -INFINITY;
-      for (int k = 0; k < n; k++) {
-        float2 a = vs.verts[v0 + k], c = vs.verts[v0 + (k + 1) % n];
-        area2 += a.x * c.y - a.y * c.x;
-        l = fminf(l, a.x); r = fmaxf(r, a.x); b = fminf(b, a.y); t = fmaxf(t, a.y);
+      if (pr.kind == MG_PRIM_NGON && n >= 20) {
+        /* regular many-gon: rigid maps keep it counter-clockwise, and a slightly generous box from two
+         * opposite vertices + the radius is enough (the box only limits where spans are searched) */
+        float2 a = vs.verts[v0], c = vs.verts[v0 + n / 2];
+        float cx = 0.5f * (a.x + c.x), cy = 0.5f * (a.y + c.y);
+        float rad = pr.radius * cam.S * 1.001f + 0.05f;
+        l = cx - rad; r = cx + rad; b = cy - rad; t = cy + rad;
+        area2 = 1.0f;
+      } else {
+        for (int k = 0; k < n; k++) {
+          float2 a = vs.verts[v0 + k], c = vs.verts[v0 + (k + 1) % n];
+          area2 += a.x * c.y - a.y * c.x;
+          l = fminf(l, a.x); r = fmaxf(r, a.x); b = fminf(b, a.y); t = fmaxf(t, a.y);
+        }
       }
       int i0 = (int)fmaxf(0.0f, floorf(l - 1.0f)), i1 = (int)fminf((float)(res_full - 1), ceilf(r + 1.0f));
       int j0 = (int)fmaxf(0.0f, floorf(b - 1.0f)), j1 = (int)fminf((float)(res_full - 1), ceilf(t + 1.0f));
@@ -331,7 +342,11 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     float sgn = vs.prims[rp0].sgn;
     float A = a.y - b.y, B = b.x - a.x;
     float C = -fmaf(A, a.x, B * a.y);
-    vs.edges[v] = make_float4(A * sgn, B * sgn, C * sgn, fminf(a.y, b.y));
+    A *= sgn; B *= sgn; C *= sgn;
+    vs.edges[v] = make_float4(A, B, C, 0.0f);
+    /* boundary column of this edge on row y: x*(y) = -(B y + C)/A = m y + q (an ESTIMATE only) */
+    float inv = (A != 0.0f) ? __fdividef(1.0f, A) : 0.0f;
+    vs.eaux[v] = make_float4(-B * inv, -C * inv, fminf(a.y, b.y), fmaxf(a.y, b.y));
   }
   __syncthreads();
   /* E: spans, one work item per (primitive, row) */
@@ -340,7 +355,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     int lo = 0, hi = nrp - 1;
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (vs.prims[mid].span0 <= w) lo = mid; else hi = mid - 1; }
     const RPrim& R = vs.prims[lo];
-    vs.spans[w] = row_span(R, vs.edges, R.row0 + (w - R.span0));
+    vs.spans[w] = row_span(R, vs.edges, vs.eaux, R.row0 + (w - R.span0));
   }
   __syncthreads();
   /* F: tile bins from the spans: one work item per (primitive, tile row) */
@@ -511,6 +526,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
     unsigned char* p = smem_raw;
     for (int v = 0; v < NV; v++) {
       vsm[v].edges = reinterpret_cast<float4*>(p); p += sizeof(float4) * (size_t)(ecap + 2 * RMAXP);
+      vsm[v].eaux = reinterpret_cast<float4*>(p); p += sizeof(float4) * (size_t)ecap;
       vsm[v].verts = reinterpret_cast<float2*>(p); p += sizeof(float2) * (size_t)ecap;
       vsm[v].prims = reinterpret_cast<RPrim*>(p); p += sizeof(RPrim) * RMAXP;
       vsm[v].spans = reinterpret_cast<short2*>(p); p += sizeof(short2) * (size_t)scap;
@@ -564,6 +580,18 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       const int Yg = ty * T + g / gpr;
       const int X0 = tx * T + (g % gpr) * 4;
       const int Y = res_out - 1 - Yg;       /* output row, 0 = top */
+      /* issue the read of the surviving frames before shading so HBM latency overlaps the ALU work */
+      uint4 pre[NV][3];
+      if ((MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_LORES3EA) &&
+          !fresh) {
+#pragma unroll
+        for (int v = 0; v < ((MODE == MG_OBS_LORESSTACK) ? NV : 1); v++) {
+          size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)v * batch : 0;
+          const uint4* ptr =
+              reinterpret_cast<const uint4*>(obs + ((plane + env) * frame_px + (size_t)Y * res_out + X0) * 12);
+          pre[v][0] = ptr[0]; pre[v][1] = ptr[1]; pre[v][2] = ptr[2];
+        }
+      }
       uint32_t col[NV][4];
 #pragma unroll
       for (int v = 0; v < NV; v++) {
@@ -583,7 +611,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           uint4* ptr = reinterpret_cast<uint4*>(obs + ((plane + env) * frame_px + (size_t)Y * res_out + X0) * 12);
           uint32_t w[12];
           if (!fresh) {
-            uint4 a = ptr[0], b = ptr[1], c = ptr[2];
+            uint4 a = pre[v][0], b = pre[v][1], c = pre[v][2];
             w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
             w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
           }
@@ -598,7 +626,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
         uint4* ptr = reinterpret_cast<uint4*>(obs + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
         uint32_t w[12];
         if (!fresh) {
-          uint4 a = ptr[0], b = ptr[1], c = ptr[2];
+          uint4 a = pre[0][0], b = pre[0][1], c = pre[0][2];
           w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
           w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
         }
@@ -657,7 +685,8 @@ static int n_views(int mode) {
 }
 
 size_t mg_raster_smem_bytes(int mode, int ecap, int scap) {
-  size_t per_view = sizeof(float4) * (size_t)(ecap + 2 * RMAXP) + sizeof(float2) * (size_t)ecap + sizeof(RPrim) * RMAXP +
+  size_t per_view = sizeof(float4) * (size_t)(ecap + 2 * RMAXP) + sizeof(float4) * (size_t)ecap +
+                    sizeof(float2) * (size_t)ecap + sizeof(RPrim) * RMAXP +
                     sizeof(short2) * (size_t)scap + sizeof(uint32_t) * RGRID * RGRID * RWORDS +
                     sizeof(int32_t) * RGRID * RGRID;
   return per_view * n_views(mode);
