@@ -43,6 +43,9 @@
 #define BG_G 231
 #define BG_B 234
 #define ZOOM 1.02
+#ifndef RASTER_MIN_BLOCKS
+#define RASTER_MIN_BLOCKS 4
+#endif
 
 struct RPrim {
   uint32_t rgb;         /* bits 0..23 colour; bit 24: stippled line */
@@ -226,18 +229,34 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   const Camera cam = make_camera(st, sc, view, res_full);
   const float px_scale = (float)res_full / 384.0f;
   /* A: vertex offsets and window-prim indices (a line loop expands to one prim per segment) */
-  if (tid == 0) {
+  if (tid < 32) {
+    /* warp 0: exclusive prefix sums of (vertex count, window-primitive count) over the draw list */
     int off = 0, rp = 0;
-    for (int p = 0; p < np; p++) {
-      s_off[p] = off;
-      s_off[MG_MAX_PRIMS + 1 + p] = rp;
-      const mg_prim_t& pr = sc.prims[p];
-      off += pr.nvert;
-      rp += (pr.kind == MG_PRIM_LINELOOP) ? pr.nvert : 1;
+    for (int base = 0; base < np; base += 32) {
+      int p = base + tid;
+      int nvv = 0, nrr = 0;
+      if (p < np) {
+        nvv = sc.prims[p].nvert;
+        nrr = (sc.prims[p].kind == MG_PRIM_LINELOOP) ? nvv : 1;
+      }
+      int iv = nvv, ir = nrr;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int tv = __shfl_up_sync(0xffffffffu, iv, d), tr = __shfl_up_sync(0xffffffffu, ir, d);
+        if (tid >= d) { iv += tv; ir += tr; }
+      }
+      if (p < np) {
+        s_off[p] = off + iv - nvv;
+        s_off[MG_MAX_PRIMS + 1 + p] = rp + ir - nrr;
+      }
+      off += __shfl_sync(0xffffffffu, iv, 31);
+      rp += __shfl_sync(0xffffffffu, ir, 31);
     }
-    s_off[np] = off;
-    s_misc[0] = off > ecap ? ecap : off;
-    s_misc[1] = rp > RMAXP ? RMAXP : rp;
+    if (tid == 0) {
+      s_off[np] = off;
+      s_misc[0] = off > ecap ? ecap : off;
+      s_misc[1] = rp > RMAXP ? RMAXP : rp;
+    }
   }
   for (int i = tid; i < RGRID * RGRID * RWORDS; i += nt) vs.tiles[i] = 0u;
   for (int i = tid; i < RGRID * RGRID; i += nt) vs.cover[i] = -1;
@@ -320,15 +339,26 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   }
   __syncthreads();
   /* D: span-table offsets (serial prefix; <= 192 entries) + oriented edge equations */
-  if (tid == 0) {
+  if (tid < 32) {
+    /* warp 0: span-table offsets = exclusive prefix sum of the row counts */
     int off = 0;
-    for (int p = 0; p < nrp; p++) {
-      RPrim& R = vs.prims[p];
-      if (off + R.nrows > scap) R.nrows = 0; /* cannot happen with the host's bound; keeps memory safe */
-      R.span0 = off;
-      off += R.nrows;
+    for (int base = 0; base < nrp; base += 32) {
+      int p = base + tid;
+      int nr = (p < nrp) ? vs.prims[p].nrows : 0;
+      int incl = nr;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (tid >= d) incl += t;
+      }
+      if (p < nrp) {
+        int start = off + incl - nr;
+        if (start + nr > scap) { vs.prims[p].nrows = 0; nr = 0; } /* cannot happen with the host's bound */
+        vs.prims[p].span0 = start;
+      }
+      off += __shfl_sync(0xffffffffu, incl, 31);
     }
-    s_misc[2] = off;
+    if (tid == 0) s_misc[2] = off > scap ? scap : off;
   }
   for (int v = tid; v < nv; v += nt) {
     int lo = 0, hi = np - 1;
@@ -504,7 +534,7 @@ __device__ __forceinline__ void stack_push(uint32_t* w, uint32_t n, bool fresh) 
 /* ------------------------------------------------------------------ kernel
  * MODE: MG_OBS_*;  SS: samples per output pixel side (4 for the LoRes modes, 1 for RAW). */
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RASTER_MIN_BLOCKS)
 k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, uint8_t* __restrict__ obs, int batch,
          int res_out, int ecap, int scap, int only_fresh) {
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
