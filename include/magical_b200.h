@@ -198,7 +198,10 @@ typedef struct {
   int32_t auto_reset;   /* 1: envs that finish an episode are reset inside mg_step
                               and the returned observation is the new episode's first */
   int32_t fast_math;    /* 0: fp64, contraction off (parity build); 1: fp64 with FMA */
-  int32_t reserved_[9];
+  int32_t reset_seed;   /* n_scenes > 1 with auto_reset: an env that finishes an episode draws its next
+                           scene on the device as hash(reset_seed, env, resets so far) % n_scenes (the
+                           reference re-randomises the layout on every reset, base_env.py:177-234) */
+  int32_t reserved_[8];
 } mg_config_t;
 
 /* One environment's simulator state in host-readable form (parity tests). */

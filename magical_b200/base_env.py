@@ -94,6 +94,7 @@ class BaseEnv(abc.ABC):
             if isinstance(entity, en.Robot):
                 self._robot = entity
             self._entities.append(entity)
+            self._builder.entities.append(entity)
             entity.setup(self._builder)
 
     def build_scene(self):

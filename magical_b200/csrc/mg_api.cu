@@ -24,7 +24,8 @@
 cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
                               int lanes_per_env, int block_threads, cudaStream_t stream);
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int batch, int auto_reset, int mode,
-                             float* reward, uint8_t* done, float* score, cudaStream_t stream);
+                             int n_scenes, uint32_t reset_seed, float* reward, uint8_t* done, float* score,
+                             cudaStream_t stream);
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
                             const int32_t* scene_ids, int first_time, cudaStream_t stream);
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
@@ -270,8 +271,8 @@ static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_de
   if (!actions_dev) return fail(MG_E_INVALID, "mg_step: null actions%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads, h->stream));
-  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, h->cfg.auto_reset, 0, reward_dev, done_dev,
-                            score_dev, h->stream));
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, h->cfg.auto_reset, 0, h->cfg.n_scenes,
+                            (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->stream));
   h->launches += 2;
   return MG_OK;
 }
@@ -298,7 +299,7 @@ int mg_render(mg_handle* h) {
 int mg_score(mg_handle* h, float* score_dev) {
   if (!h || !score_dev) return fail(MG_E_INVALID, "mg_score: null argument%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, 0, 1, nullptr, nullptr, score_dev, h->stream));
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, 0, 1, 1, 0u, nullptr, nullptr, score_dev, h->stream));
   h->launches++;
   return MG_OK;
 }

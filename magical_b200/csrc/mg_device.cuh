@@ -32,7 +32,7 @@ struct __align__(16) CEntry {
 /* Per-environment simulator state in HBM: one contiguous, 16-byte-aligned record that a warp (or
  * half-warp) streams in and out with 128-bit loads. */
 struct __align__(16) EnvState {
-  int32_t scene, episode_steps, stamp, n_cache, overflow, fresh, last_contacts, pad_;
+  int32_t scene, episode_steps, stamp, n_cache, overflow, fresh, last_contacts, resets;
   double4 V[MG_MAX_BODIES];  /* vx, vy, w, - */
   double4 Bv[MG_MAX_BODIES]; /* bias velocities vbx, vby, wb, - (consumed by the next position update) */
   double4 P[MG_MAX_BODIES];  /* px, py, angle, - */

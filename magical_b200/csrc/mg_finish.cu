@@ -231,9 +231,14 @@ __device__ static void reset_state(EnvState& st, const DeviceScene* ds, int scen
 }
 
 /* mode 0: full step tail; mode 1: score of the current state only (mg_score) */
+__device__ __forceinline__ uint32_t mix32(uint32_t x) { /* lowbias32 integer hash */
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
 __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, int batch,
-                         int auto_reset, int mode, float* __restrict__ reward, uint8_t* __restrict__ done,
-                         float* __restrict__ score) {
+                         int auto_reset, int mode, int n_scenes, uint32_t reset_seed, float* __restrict__ reward,
+                         uint8_t* __restrict__ done, float* __restrict__ score) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= batch) return;
   EnvState& st = states[env];
@@ -262,7 +267,15 @@ __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __res
   if (reward) reward[env] = (float)rew;
   if (done) done[env] = d ? 1 : 0;
   if (score) score[env] = (float)s;
-  if (d && auto_reset) reset_state(st, ds, st.scene);
+  if (d && auto_reset) {
+    int scene = st.scene;
+    if (n_scenes > 1) {
+      /* randomised variants: the next episode plays a freshly drawn scene of the pre-sampled pool */
+      const int resets = ++st.resets;
+      scene = (int)(mix32(mix32(reset_seed ^ mix32((uint32_t)env)) + (uint32_t)resets) % (uint32_t)n_scenes);
+    }
+    reset_state(st, scenes + scene, scene);
+  }
 }
 
 /* explicit reset of selected envs (env_ids == nullptr: all), optional new scene index per env */
@@ -282,10 +295,11 @@ __global__ void k_reset(EnvState* __restrict__ states, const DeviceScene* __rest
 }
 
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int batch, int auto_reset, int mode,
-                             float* reward, uint8_t* done, float* score, cudaStream_t stream) {
+                             int n_scenes, uint32_t reset_seed, float* reward, uint8_t* done, float* score,
+                             cudaStream_t stream) {
   int threads = 128;
-  k_finish<<<(batch + threads - 1) / threads, threads, 0, stream>>>(states, scenes, batch, auto_reset, mode, reward,
-                                                                    done, score);
+  k_finish<<<(batch + threads - 1) / threads, threads, 0, stream>>>(states, scenes, batch, auto_reset, mode, n_scenes,
+                                                                    reset_seed, reward, done, score);
   return cudaGetLastError();
 }
 

@@ -186,14 +186,18 @@ class Robot(Entity):
                 max_force=pv.robot_finger_max_force))
         # collision shapes (entities.py:356-375): all in the robot's filter
         # group so robot parts never collide with each other
-        b.add_shapes(body, [(sc.SHAPE_CIRCLE, [(0.0, 0.0)], R, 0.5,
-                             ROBOT_GROUP)], robot_group=True)
+        # reference `Entity.bodies` / `Entity.shapes` order (entities.py:247-374)
+        self.body_ids = [body, control, *eyes, *fingers]
+        self.cgroup_ids = [b.add_shapes(
+            body, [(sc.SHAPE_CIRCLE, [(0.0, 0.0)], R, 0.5, ROBOT_GROUP)],
+            robot_group=True)]
         finger_hulls = []
         for finger, verts in zip(fingers, finger_verts):
             hulls = [gtools.convex_hull(sub) for sub in verts]
             finger_hulls.append(hulls)
-            b.add_shapes(finger, [(sc.SHAPE_POLY, h, 0.0, 5.0, ROBOT_GROUP)
-                                  for h in hulls], robot_group=True)
+            self.cgroup_ids.append(b.add_shapes(
+                finger, [(sc.SHAPE_POLY, h, 0.0, 5.0, ROBOT_GROUP)
+                         for h in hulls], robot_group=True))
 
         # graphics (entities.py:377-437), painter's order preserved
         dark = to_u8(darken_rgb(GREY))
@@ -233,10 +237,13 @@ class ArenaBoundaries(Entity):
                (self.right + rad, self.top + rad),
                (self.right + rad, self.bottom - rad),
                (self.left - rad, self.bottom - rad)]
+        self.body_ids = []
+        self.cgroup_ids = []
         for start, end in zip(pts, pts[1:] + pts[:1]):
             # each wall is its own collision group: broadphase tests them
             # individually
-            b.add_shapes(-1, [(sc.SHAPE_SEGMENT, [start, end], rad, 0.8, 0)])
+            self.cgroup_ids.append(b.add_shapes(
+                -1, [(sc.SHAPE_SEGMENT, [start, end], rad, 0.8, 0)]))
         w = self.right - self.left
         h = self.top - self.bottom
         rect = [(-w / 2, h / 2), (w / 2, h / 2), (w / 2, -h / 2),
@@ -329,6 +336,8 @@ class Shape(Entity):
                                                                 short_side))]
         body = b.add_body(self.mass, moment, self.init_pos, self.init_angle)
         cgroup = b.add_shapes(body, shapes)
+        self.body_ids = [body]
+        self.cgroup_ids = [cgroup]
         # table friction: force-capped pivot + gear against the static body
         # (entities.py:703-711)
         b.add_joint(sc.JOINT_PIVOT, -1, body, max_bias=0.0,
@@ -366,10 +375,29 @@ class GoalRegion(Entity):
     def centre(self):
         return (self.x + self.w / 2, self.y - self.h / 2)
 
+    def _corners(self, cx, cy):
+        return [(px + cx, py + cy)
+                for px, py in make_rect_points(self.w, self.h)]
+
+    def move_to(self, b, cx, cy):
+        """Re-centre the region (reset-time randomisation moves the goal's
+        static body, geom.py:362-384; its geoms follow in `pre_draw`,
+        entities.py:883-886)."""
+        cx, cy = float(cx), float(cy)
+        self.x, self.y = cx - self.w / 2, cy + self.h / 2
+        goal = b.goals[self.goal_index]
+        goal['cx'], goal['cy'] = cx, cy
+        pts = self._corners(cx, cy)
+        for pi in self.prim_ids:
+            v0 = b.prims[pi]['vert0']
+            b.dverts[v0:v0 + 4] = pts
+
     def setup(self, b):
         cx, cy = self.centre
-        pts = [(px + cx, py + cy)
-               for px, py in make_rect_points(self.w, self.h)]
+        pts = self._corners(cx, cy)
+        self.body_ids = []
+        self.cgroup_ids = []
+        self.prim_ids = (len(b.prims), len(b.prims) + 1)
         b.add_poly_prim(pts, to_u8(lighten_rgb(self.base_colour, times=2)))
         b.add_lineloop_prim(pts, to_u8(self.base_colour),
                             250 * GOAL_LINE_THICKNESS, stipple=0x00FF)

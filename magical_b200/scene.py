@@ -80,7 +80,8 @@ scene_dt = np.dtype([
 
 config_dt = np.dtype([('device', 'i4'), ('batch', 'i4'), ('n_scenes', 'i4'),
                       ('obs_mode', 'i4'), ('res', 'i4'), ('auto_reset', 'i4'),
-                      ('fast_math', 'i4'), ('reserved_', 'i4', 9)], align=True)
+                      ('fast_math', 'i4'), ('reset_seed', 'i4'),
+                      ('reserved_', 'i4', 8)], align=True)
 
 state_dt = np.dtype([
     ('n_bodies', 'i4'), ('n_joints', 'i4'), ('n_contacts', 'i4'),
@@ -111,6 +112,7 @@ class SceneBuilder:
         self.dverts = []
         self.goals = []
         self.blocks = []
+        self.entities = []  # Entity objects in insertion order (placement)
         self.n_labels = 0
         self.robot = None
         self._star_group = 999  # Entity.generate_group_id, entities.py:60-66

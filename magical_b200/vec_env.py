@@ -68,7 +68,8 @@ class MagicalVecEnv:
         cfg = _native.make_config(device=device, batch=self.batch,
                                   n_scenes=self.n_scenes, obs_mode=self.mode,
                                   res=res, auto_reset=int(self.auto_reset),
-                                  fast_math=0)
+                                  fast_math=0,
+                                  reset_seed=int(self.rng.randint(1 << 31)))
         import ctypes
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):

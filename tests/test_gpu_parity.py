@@ -232,3 +232,62 @@ def test_auto_reset_and_done_mask(built):
             assert torch.equal(obs, obs0)
             assert int(venv.get_state(2)['episode_steps']) == 0
     venv.close()
+
+
+@pytest.mark.parametrize('env_id', ['MatchRegions-TestAll-LoResStack-v0',
+                                    'ClusterShape-TestAll-LoRes4E-v0',
+                                    'FindDupe-TestJitter-LoRes4E-v0'])
+def test_randomised_variant_pool_bit_exact(built, env_id):
+    """Randomised Test* variants: a pool of host-sampled scenes (placement
+    restating geom.py:116-341), each env bound to one of them; physics and
+    observation bit-exact against the oracle stepping the same scene."""
+    import torch
+    import magical_b200 as magical
+    from oracle_lib import OracleEnv
+    batch, n_scenes = 12, 5
+    venv = magical.make_vec(env_id, batch, auto_reset=False,
+                            n_scenes=n_scenes, seed=13)
+    scene_ids = np.arange(batch) % n_scenes
+    obs = venv.reset(scene_ids=scene_ids)
+    watch = [1, 4, 7, 10]
+    oracles = {e: OracleEnv(venv.scenes[scene_ids[e]], det_sincos=True)
+               for e in watch}
+    rng = np.random.RandomState(2)
+    for t in range(30):
+        acts = rng.randint(0, 18, size=batch).astype(np.int32)
+        obs, rew, done, info = venv.step(torch.from_numpy(acts).cuda())
+        for e, orc in oracles.items():
+            orc.step(int(acts[e]))
+            st, ost = venv.get_state(e), orc.state()
+            nb = int(st['n_bodies'])
+            assert int(st['scene']) == scene_ids[e]
+            assert int(st['overflow']) == 0
+            assert np.array_equal(st['pos'][:nb], ost['pos'][:nb]), (t, e)
+            assert np.array_equal(st['angle'][:nb], ost['angle'][:nb]), (t, e)
+    obs = obs.cpu().numpy()
+    for e, orc in oracles.items():
+        ego = orc.render_lores(1)
+        got = obs[1, e, :, :, 9:12] if obs.ndim == 5 else obs[e, :, :, 9:12]
+        assert np.array_equal(got, ego), (env_id, e)
+    venv.close()
+
+
+def test_auto_reset_redraws_scene_from_pool(built):
+    """With a scene pool, an env that finishes an episode continues on a
+    scene drawn on the device; every env stays on a valid pool index and the
+    draws differ between envs."""
+    import torch
+    import magical_b200 as magical
+    batch, n_scenes = 64, 8
+    venv = magical.make_vec('MoveToRegion-TestAll-LoRes4E-v0', batch,
+                            auto_reset=True, n_scenes=n_scenes, seed=3)
+    venv.reset()
+    rng = np.random.RandomState(0)
+    for t in range(41):
+        acts = rng.randint(0, 18, size=batch).astype(np.int32)
+        venv.step(torch.from_numpy(acts).cuda())
+    scenes = [int(venv.get_state(e)['scene']) for e in range(batch)]
+    assert all(0 <= s < n_scenes for s in scenes)
+    assert len(set(scenes)) > 2
+    assert int(venv.get_state(5)['episode_steps']) == 1
+    venv.close()
