@@ -19,10 +19,15 @@
 #include <vector>
 
 #include "mg_device.cuh"
+#include "mg_physics_tpe.h"
 #include "mg_sincos.h"
 
 cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
                               int lanes_per_env, int block_threads, cudaStream_t stream);
+cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
+                                  const TpeLayout* L, double* spill, cudaStream_t stream);
+size_t mg_tpe_smem_bytes(const TpeLayout* L);
+size_t mg_tpe_spill_doubles_per_env(const TpeLayout* L);
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int batch, int auto_reset, int mode,
                              int n_scenes, uint32_t reset_seed, float* reward, uint8_t* done, float* score,
                              cudaStream_t stream);
@@ -47,6 +52,9 @@ struct mg_handle {
   int scap;             /* span-table rows the rasteriser reserves per view */
   int lanes_per_env;    /* 16: two environments share a warp in K1; 32: one warp per environment */
   int block_threads;    /* K1 block size: 512 = one phase-aligned block per SM, 128 = small blocks */
+  int use_tpe;          /* K1 variant: 1 = thread per environment (mg_physics_tpe.h), 0 = lanes per environment */
+  TpeLayout tpe;        /* private-word layout of the thread-per-environment kernel */
+  double* d_spill;      /* its contact spill area */
   int64_t launches;
 };
 
@@ -177,11 +185,38 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
     if (v == 128 || v == 512) h->block_threads = v;
   }
   h->obs_bytes = obs_bytes_for(cfg, res_out);
+  /* K1 variant: every MAGICAL scene has the canonical robot + drag-jointed blocks structure and runs one
+   * environment per thread; anything else (hand-built scenes) falls back to the cooperative kernel */
+  h->use_tpe = 1;
+  int max_slots = 0, max_blocks = 0, max_groups = 0;
+  for (int i = 0; i < cfg->n_scenes; i++) {
+    if (!host[i].aux.tpe_ok) h->use_tpe = 0;
+    if (host[i].aux.tpe_nslots > max_slots) max_slots = host[i].aux.tpe_nslots;
+    if (host[i].aux.tpe_nblocks > max_blocks) max_blocks = host[i].aux.tpe_nblocks;
+    if (scenes[i].n_cgroups > max_groups) max_groups = scenes[i].n_cgroups;
+  }
+  if (const char* ev = getenv("MG_PHYSICS")) {
+    if (!strcmp(ev, "warp")) h->use_tpe = 0;
+  }
+  if (h->use_tpe) {
+    int kcon = 6;
+    if (const char* ev = getenv("MG_TPE_KCON")) kcon = atoi(ev);
+    if (kcon < 1) kcon = 1;
+    if (kcon > TPE_MAX_CONTACTS) kcon = TPE_MAX_CONTACTS;
+    int nitems = 12;
+    if (const char* ev = getenv("MG_TPE_NITEMS")) nitems = atoi(ev);
+    h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, kcon, nitems);
+    while (mg_tpe_smem_bytes(&h->tpe) > 200 * 1024 && kcon > 1)
+      h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, --kcon, nitems);
+  }
   cudaError_t e;
   if ((e = cudaMalloc(&h->d_states, sizeof(EnvState) * (size_t)cfg->batch)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_scenes, sizeof(DeviceScene) * (size_t)cfg->n_scenes)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
-      (e = cudaMalloc(&h->d_scene_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess) {
+      (e = cudaMalloc(&h->d_scene_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
+      (h->use_tpe && mg_tpe_spill_doubles_per_env(&h->tpe) > 0 &&
+       (e = cudaMalloc(&h->d_spill, sizeof(double) * mg_tpe_spill_doubles_per_env(&h->tpe) * (size_t)cfg->batch)) !=
+           cudaSuccess)) {
     mg_destroy(h);
     return fail(MG_E_NOMEM, "mg_create: cudaMalloc: %s", cudaGetErrorString(e));
   }
@@ -219,6 +254,7 @@ int mg_destroy(mg_handle* h) {
   cudaFree(h->d_scenes);
   cudaFree(h->d_ids);
   cudaFree(h->d_scene_ids);
+  cudaFree(h->d_spill);
   delete h;
   return MG_OK;
 }
@@ -270,7 +306,11 @@ int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* sce
 static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
   if (!actions_dev) return fail(MG_E_INVALID, "mg_step: null actions%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads, h->stream));
+  if (h->use_tpe)
+    CUDA_TRY(mg_launch_physics_tpe(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, &h->tpe, h->d_spill, h->stream));
+  else
+    CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads,
+                               h->stream));
   CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, h->cfg.auto_reset, 0, h->cfg.n_scenes,
                             (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->stream));
   h->launches += 2;

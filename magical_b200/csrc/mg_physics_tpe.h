@@ -1,0 +1,1023 @@
+/*
+ * mg_physics_tpe.h — K1 body, "thread per environment" form: one env-step (Robot.set_action + 10 x
+ * (Robot.update + Chipmunk-equivalent space step)) of ONE environment executed by ONE thread.
+ *
+ * Replaces the same reference calls as mg_physics.cu (entities.py:439-479, base_env.py:236-243 and
+ * pymunk's Space.step).  Why this shape on B200: the sequential-impulse solver is a dependent chain
+ * (10 sub-steps x 10 iterations x (contacts, then the robot's 10 joints which all touch the robot
+ * body)), so lanes that cooperate on one environment mostly wait for each other (ncu, round 1: 7 of 32
+ * lanes active, 25 % of stall samples at barriers).  Here every lane of a warp owns a DIFFERENT
+ * environment, all lanes walk the same instruction stream (environments of a batch share a scene
+ * structure), and nothing is ever exchanged between lanes, so there are no barriers at all.
+ *
+ * Memory plan per environment
+ *   - private 8-byte words in shared memory, laid out [word][lane] (conflict-free, dynamic indexing is
+ *     free): velocities + bias velocities + pose/rotation of every body that owns collision shapes,
+ *     the blocks' drag-joint accumulators, the motion-bound table of the separation cache and the
+ *     sub-step's solver contacts (sharing their words with the broadphase group boxes, which are dead
+ *     by the time contacts are born);
+ *   - registers: everything that belongs to the robot's joint chain (control / eye bodies, the ten
+ *     joint accumulators, per-sub-step pin frames, biases, motor rates) -- the chain is the same in every
+ *     MAGICAL scene (entities.py:238-354), so it is unrolled with static indexing;
+ *   - the environment's record in HBM/L2 is touched at the start and the end of the launch, plus the
+ *     small contact cache once per sub-step.
+ *
+ * The arithmetic of every formula is the literal operation order of mg_physics.cu / oracle/mgo_physics.c
+ * (bit-exact parity); only the *schedule* differs.  The Gauss-Seidel order is the reference's: contacts in
+ * canonical arbiter order, then joints; joints of different bodies' drag pairs and the robot chain share
+ * no dynamic body, so their relative order is immaterial (they commute exactly).
+ *
+ * The file compiles for the host as well (tests/host/tpe_host.cpp), which is how the CPU test-suite
+ * checks this very source against the oracle without a GPU.
+ */
+#ifndef MG_PHYSICS_TPE_H
+#define MG_PHYSICS_TPE_H
+
+#include "mg_device.cuh"
+#include "mg_narrowphase.h"
+#include "mg_sincos.h"
+
+#define TPE_CON_WORDS 14
+#define TPE_MAX_CONTACTS 16 /* solver contacts per sub-step (private words first, then the spill area) */
+#define TPE_NO_SLOT 15
+
+#if defined(__CUDACC__)
+#define MG_HDM __host__ __device__ __forceinline__
+#else
+#define MG_HDM inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define TPE_LDG(p) __ldg(p)
+#define TPE_CTZ(x) (__ffs((int)(x)) - 1)
+#else
+#define TPE_LDG(p) (*(p))
+#define TPE_CTZ(x) __builtin_ctz(x)
+#endif
+
+MG_HD float tpe_d2f_ru(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2float_ru(x);
+#else
+  float f = (float)x;
+  if ((double)f < x) f = nextafterf(f, INFINITY);
+  return f;
+#endif
+}
+MG_HD float tpe_d2f_rd(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2float_rd(x);
+#else
+  float f = (float)x;
+  if ((double)f > x) f = nextafterf(f, -INFINITY);
+  return f;
+#endif
+}
+MG_HD float tpe_fadd_ru(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_ru(a, b);
+#else
+  return tpe_d2f_ru((double)a + (double)b); /* the double sum of two floats is exact */
+#endif
+}
+MG_HD float tpe_fadd_rd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rd(a, b);
+#else
+  return tpe_d2f_rd((double)a + (double)b);
+#endif
+}
+
+/* Private-word layout, uniform for a launch (sized for the largest scene of the handle). */
+struct TpeLayout {
+  int nslots;   /* velocity slots incl. the static dummy */
+  int nblocks;
+  int off_bv, off_pr, off_bj, off_path, off_con;
+  int kcon;     /* contacts that fit in the private words */
+  int off_it, nitems; /* narrowphase work items of the sub-step (one word each) */
+  int words;    /* 8-byte words per environment */
+};
+
+static inline TpeLayout tpe_make_layout(int nslots, int nblocks, int ncgroups, int kcon, int nitems) {
+  TpeLayout L;
+  L.nslots = nslots;
+  L.nblocks = nblocks;
+  L.off_bv = nslots * 3;
+  L.off_pr = L.off_bv + nslots * 3;
+  L.off_bj = L.off_pr + (nslots - 1) * 5;
+  L.off_path = L.off_bj + nblocks * 4;
+  L.off_con = L.off_path + (nslots + 1) / 2;
+  int con_words = kcon * TPE_CON_WORDS;
+  if (con_words < ncgroups * 2) con_words = ncgroups * 2; /* float4 group boxes share the contact words */
+  L.kcon = con_words / TPE_CON_WORDS;
+  if (L.kcon > TPE_MAX_CONTACTS) L.kcon = TPE_MAX_CONTACTS;
+  L.off_it = L.off_con + con_words;
+  L.nitems = nitems < 1 ? 1 : nitems;
+  L.words = L.off_it + L.nitems;
+  return L;
+}
+
+/* accessors over one environment's private words; S = distance (in words) between consecutive words */
+template <int S>
+struct Tpe {
+  double* wd;
+  float* wf;
+  TpeLayout L;
+  double* spill; /* [TPE_MAX_CONTACTS - kcon][TPE_CON_WORDS] contiguous, or null */
+  uint64_t slotmap;
+  int static_slot;
+  MG_HDM double& V(int s, int k) const { return wd[(s * 3 + k) * S]; }
+  MG_HDM double& Bv(int s, int k) const { return wd[(L.off_bv + s * 3 + k) * S]; }
+  MG_HDM double& PR(int s, int k) const { return wd[(L.off_pr + s * 5 + k) * S]; } /* x y angle cos sin */
+  MG_HDM double& BJ(int b, int k) const { return wd[(L.off_bj + b * 4 + k) * S]; } /* pivot x,y  gear  gear bias */
+  MG_HDM float& path(int s) const { return wf[(L.off_path * 2 + s) * S]; }
+  MG_HDM float& gbb(int g, int k) const { return wf[(L.off_con * 2 + g * 4 + k) * S]; }
+  MG_HDM uint64_t& IT(int k) const { return reinterpret_cast<uint64_t*>(wd)[(L.off_it + k) * S]; }
+  MG_HDM int slot(int body) const { /* body index or <0 / MG_MAX_BODIES for the static body */
+    return (body < 0 || body >= MG_MAX_BODIES) ? static_slot : (int)((slotmap >> (4 * body)) & 15u);
+  }
+};
+
+/* reference to the words of contact c (private words or spill area) */
+struct TpeCon {
+  double* p;
+  int st;
+  MG_HDM double& operator[](int k) const { return p[k * st]; }
+};
+template <int S>
+MG_HD TpeCon tpe_con(const Tpe<S>& T, int c) {
+  TpeCon r;
+  if (c < T.L.kcon) { r.p = &T.wd[(T.L.off_con + c * TPE_CON_WORDS) * S]; r.st = S; }
+  else { r.p = T.spill + (c - T.L.kcon) * TPE_CON_WORDS; r.st = 1; }
+  return r;
+}
+/* contact words: 0,1 r1 | 2,3 r2 | 4,5 n | 6 nMass | 7 tMass | 8 bias | 9 jn | 10 jt | 11 jb | 12 u | 13 ids */
+MG_HD double tpe_pack_ids(unsigned hash, int sa, int sb, int ba, int bb, int first) {
+  unsigned long long v = (unsigned long long)hash | ((unsigned long long)(sa & 0xFF) << 32) |
+                         ((unsigned long long)(sb & 0xFF) << 40) | ((unsigned long long)(ba & 0x1F) << 48) |
+                         ((unsigned long long)(bb & 0x1F) << 53) | ((unsigned long long)(first & 1) << 58);
+  double d;
+  memcpy(&d, &v, 8);
+  return d;
+}
+MG_HD unsigned long long tpe_unpack_ids(double d) {
+  unsigned long long v;
+  memcpy(&v, &d, 8);
+  return v;
+}
+
+
+#if defined(TPE_STATS) && !defined(__CUDACC__)
+extern long tpe_stats[8]; /* host instrumentation: 0 sub-steps, 1 items, 2 items with contacts, 3 box-overlapping group pairs, 4 sep-skipped */
+#define TPE_STAT(i) (tpe_stats[i]++)
+#else
+#define TPE_STAT(i) ((void)0)
+#endif
+#define TPE_IT_LAST (1ull << 24)
+#define TPE_IT_CONT (1ull << 25)
+#define TPE_NL(S) ((S) > 1 ? 32 : 1) /* lanes that cooperate: the warp on the device, one lane on the host */
+
+MG_HD bool tpe_f4_overlap(float4 a, float4 b) { return a.x <= b.z && b.x <= a.z && a.y <= b.w && b.y <= a.w; }
+/* gap between two disjoint boxes (exact in double): a lower bound of the distance of their contents */
+MG_HD double tpe_f4_gap(float4 a, float4 b) {
+  return dmaxf(dmaxf((double)b.x - (double)a.z, (double)a.x - (double)b.z),
+               dmaxf((double)b.y - (double)a.w, (double)a.y - (double)b.w));
+}
+
+/* warp cooperation primitives; on the host (S == 1) the warp is a single lane */
+template <int S> MG_HD int tpe_lane() {
+#if defined(__CUDA_ARCH__)
+  return S > 1 ? (int)(threadIdx.x & 31) : 0;
+#else
+  return 0;
+#endif
+}
+template <int S> MG_HD int tpe_shfl(int v, int src) {
+#if defined(__CUDA_ARCH__)
+  return S > 1 ? __shfl_sync(0xffffffffu, v, src) : v;
+#else
+  (void)src; return v;
+#endif
+}
+template <int S> MG_HD double tpe_shfld(double v, int src) {
+#if defined(__CUDA_ARCH__)
+  return S > 1 ? __shfl_sync(0xffffffffu, v, src) : v;
+#else
+  (void)src; return v;
+#endif
+}
+template <int S> MG_HD uint64_t tpe_shfl64(uint64_t v, int src) {
+#if defined(__CUDA_ARCH__)
+  return S > 1 ? (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)v, src) : v;
+#else
+  (void)src; return v;
+#endif
+}
+template <int S> MG_HD int tpe_scan_incl(int v) {
+#if defined(__CUDA_ARCH__)
+  if (S > 1) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += t;
+    }
+  }
+#endif
+  return v;
+}
+template <int S> MG_HD int tpe_max(int v) {
+#if defined(__CUDA_ARCH__)
+  if (S > 1) return __reduce_max_sync(0xffffffffu, v);
+#endif
+  return v;
+}
+
+template <int S>
+MG_HD ShapeView tpe_view(const Tpe<S>& T, const DeviceScene* ds, int si) {
+  const mg_shape_t& sh = ds->s.shapes[si];
+  ShapeView v;
+  v.kind = sh.kind;
+  v.nvert = sh.nvert;
+  v.lv = &ds->s.cverts[sh.vert0][0];
+  v.ln = &ds->aux.cnorm[sh.vert0][0];
+  v.radius = sh.radius;
+  v.index = si;
+  const int b = sh.body;
+  if (b >= 0) {
+    const int s = T.slot(b);
+    v.px = T.PR(s, 0); v.py = T.PR(s, 1); v.rc = T.PR(s, 3); v.rs = T.PR(s, 4);
+  } else {
+    v.rc = 1.0; v.rs = 0.0; v.px = 0.0; v.py = 0.0;
+  }
+  return v;
+}
+
+/* conservative fp32 box of one shape (outward rounding of the exact fp64 box) */
+template <int S>
+MG_HD float4 tpe_shape_box(const Tpe<S>& T, const DeviceScene* ds, int si) {
+  if (ds->s.shapes[si].body >= 0) {
+    ShapeView v = tpe_view(T, ds, si);
+    double bb[4];
+    sv_bb(v, bb);
+    return make_float4(tpe_d2f_rd(bb[0]), tpe_d2f_rd(bb[1]), tpe_d2f_ru(bb[2]), tpe_d2f_ru(bb[3]));
+  }
+  return make_float4(ds->aux.static_bb[si][0], ds->aux.static_bb[si][1], ds->aux.static_bb[si][2],
+                     ds->aux.static_bb[si][3]);
+}
+
+/* Exact narrowphase of one shape pair (kinds already ordered).  When the exact boxes are disjoint the
+ * gap between them is a valid lower bound of the shapes' distance and is reported as the margin. */
+template <int S>
+MG_HD_NOINLINE void tpe_narrow_pair(const Tpe<S>* Tp, const DeviceScene* ds, int ia, int ib, Manifold* out) {
+  const Tpe<S>& T = *Tp;
+  ShapeView va = tpe_view(T, ds, ia), vb = tpe_view(T, ds, ib);
+  double bba[4], bbb[4];
+  sv_bb(va, bba);
+  sv_bb(vb, bbb);
+  Manifold m;
+  m.count = 0;
+  m.margin = -1.0;
+  m.n = D2(0, 0);
+  if (bb_intersects(bba, bbb)) {
+    mg_collide(va, vb, bba, bbb, m);
+  } else {
+    m.margin = dmaxf(dmaxf(bbb[0] - bba[2], bba[0] - bbb[2]), dmaxf(bbb[1] - bba[3], bba[1] - bbb[3]));
+  }
+  *out = m;
+}
+
+/* v += j*m_inv; w += i_inv * cross(r, j) on a velocity slot (static dummy: zero inverse mass) */
+#define TPE_APPLY(ARR, s, m_inv, i_inv, jx, jy, rx, ry)           \
+  do {                                                            \
+    double tx_ = T.ARR(s, 0), ty_ = T.ARR(s, 1), tz_ = T.ARR(s, 2); \
+    tx_ = tx_ + (jx) * (m_inv);                                   \
+    ty_ = ty_ + (jy) * (m_inv);                                   \
+    tz_ += (i_inv) * ((rx) * (jy) - (ry) * (jx));                 \
+    T.ARR(s, 0) = tx_; T.ARR(s, 1) = ty_; T.ARR(s, 2) = tz_;      \
+  } while (0)
+
+struct TpeJC {
+  double ma, ia, mb, ib, c0, c1, c2, c3;
+};
+MG_HD TpeJC tpe_jc(const DeviceScene* ds, int j) {
+  const double* p = &ds->aux.jc[j][0];
+  TpeJC r;
+  r.ma = TPE_LDG(p + 0); r.ia = TPE_LDG(p + 1); r.mb = TPE_LDG(p + 2); r.ib = TPE_LDG(p + 3);
+  r.c0 = TPE_LDG(p + 4); r.c1 = TPE_LDG(p + 5); r.c2 = TPE_LDG(p + 6); r.c3 = TPE_LDG(p + 7);
+  return r;
+}
+
+/* the three purely angular joint kinds of the chain on explicit angular velocities */
+MG_HD void tpe_gear(const TpeJC& c, double bias, double& acc, double& wa, double& wb) {
+  double wr = wb * c.c2 - wa;
+  double jj = (bias - wr) * c.c0;
+  const double jOld = acc;
+  const double jNew = dclamp(jOld + jj, -c.c1, c.c1);
+  acc = jNew;
+  jj = jNew - jOld;
+  double da = jj * c.ia;
+  da = da * c.c3;
+  wa = wa - da;
+  wb = wb + jj * c.ib;
+}
+MG_HD void tpe_limit(const TpeJC& c, double bias, double& acc, double& wa, double& wb) {
+  if (!bias) return;
+  double wr = wb - wa;
+  double jj = -(bias + wr) * c.c0;
+  const double lo = (bias < 0.0) ? 0.0 : -c.c1;
+  const double hi = (!(bias < 0.0)) ? 0.0 : c.c1;
+  const double jOld = acc;
+  const double jNew = dclamp(jOld + jj, lo, hi);
+  acc = jNew;
+  jj = jNew - jOld;
+  double da = jj * c.ia;
+  wa = wa - da;
+  wb = wb + jj * c.ib;
+}
+MG_HD void tpe_motor(const TpeJC& c, double rate, double& acc, double& wa, double& wb) {
+  double wr = wb - wa;
+  wr = wr + rate;
+  double jj = -wr * c.c0;
+  const double jOld = acc;
+  const double jNew = dclamp(jOld + jj, -c.c1, c.c1);
+  acc = jNew;
+  jj = jNew - jOld;
+  double da = jj * c.ia;
+  wa = wa - da;
+  wb = wb + jj * c.ib;
+}
+MG_HD void tpe_spring(const TpeJC& c, double& target, double& acc, double& wa, double& wb) {
+  double wrn = wa - wb;
+  double w_damp = (target - wrn) * c.c2;
+  target = wrn + w_damp;
+  double j_damp = w_damp * c.c0;
+  acc += j_damp;
+  wa = wa + j_damp * c.ia;
+  wb = wb - j_damp * c.ib;
+}
+struct TpePin {
+  double r1x, r1y, r2x, r2y, nx, ny, nMass, bias;
+};
+MG_HD void tpe_pin(const TpeJC& c, const TpePin& pn, double& acc, double& vax, double& vay, double& wa, double& vbx,
+                   double& vby, double& wb) {
+  d2 r1 = D2(pn.r1x, pn.r1y), r2 = D2(pn.r2x, pn.r2y);
+  d2 n = D2(pn.nx, pn.ny);
+  d2 v1 = dadd(D2(vax, vay), dmul(dperp(r1), wa));
+  d2 v2 = dadd(D2(vbx, vby), dmul(dperp(r2), wb));
+  double vrn = ddot(dsub(v2, v1), n);
+  double jn = (pn.bias - vrn) * pn.nMass;
+  double jnOld = acc;
+  double jnNew = dclamp(jnOld + jn, -c.c1, c.c1);
+  acc = jnNew;
+  jn = jnNew - jnOld;
+  double jx = n.x * jn, jy = n.y * jn;
+  vax = vax + (-jx) * c.ma; vay = vay + (-jy) * c.ma;
+  wa += c.ia * (r1.x * (-jy) - r1.y * (-jx));
+  vbx = vbx + jx * c.mb; vby = vby + jy * c.mb;
+  wb += c.ib * (r2.x * jy - r2.y * jx);
+}
+
+/* One env-step of one environment.  `sep` is per-thread scratch of MG_MAX_BPAIRS floats. */
+template <int S>
+MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* __restrict__ ds, int action, float* sep,
+                         const bool live) {
+  const mg_scene_t& sc = ds->s;
+  const mg_scene_aux_t& ax = ds->aux;
+  const double dt = MG_DT;
+  /* lanes beyond the batch (`live` == false) stay in the warp for the cooperative narrowphase: they read a
+   * valid record, do no per-environment work (all trip counts zero) and never store to global memory */
+  const int nblk = live ? ax.tpe_nblocks : 0;
+  const int nslots = live ? ax.tpe_nslots : 1;
+  T.slotmap = ax.tpe_slotmap;
+  T.static_slot = nslots - 1;
+  const int robot = sc.robot_body, control = sc.control_body;
+  const int eye0 = sc.eye_body[0], eye1 = sc.eye_body[1];
+  const int fb0 = sc.finger_body[0], fb1 = sc.finger_body[1];
+  const int s_robot = T.slot(robot), s_f0 = T.slot(fb0), s_f1 = T.slot(fb1);
+  const int jr0 = ax.tpe_jr0;
+  const int nbp = live ? sc.n_bpairs : 0, ncg = live ? sc.n_cgroups : 0;
+
+  int stamp = G->stamp, n_cache = live ? G->n_cache : 0, overflow = G->overflow;
+
+  /* ---- load: shaped bodies into the private words, chain bodies / accumulators into registers */
+  for (int s = 0; s < nslots - 1; s++) {
+    const int b = ax.tpe_slot_body[s];
+    const double4 v = G->V[b], bv = G->Bv[b], p = G->P[b];
+    const double2 r = G->R[b];
+    T.V(s, 0) = v.x; T.V(s, 1) = v.y; T.V(s, 2) = v.z;
+    T.Bv(s, 0) = bv.x; T.Bv(s, 1) = bv.y; T.Bv(s, 2) = bv.z;
+    T.PR(s, 0) = p.x; T.PR(s, 1) = p.y; T.PR(s, 2) = p.z; T.PR(s, 3) = r.x; T.PR(s, 4) = r.y;
+    T.path(s) = 0.0f;
+  }
+  {
+    const int s = nslots - 1;
+    T.V(s, 0) = 0.0; T.V(s, 1) = 0.0; T.V(s, 2) = 0.0;
+    T.Bv(s, 0) = 0.0; T.Bv(s, 1) = 0.0; T.Bv(s, 2) = 0.0;
+    T.path(s) = 0.0f;
+  }
+  for (int k = 0; k < nblk; k++) {
+    const double2 ap = G->jacc[ax.tpe_bj_pivot[k]];
+    T.BJ(k, 0) = ap.x; T.BJ(k, 1) = ap.y;
+    T.BJ(k, 2) = G->jacc[ax.tpe_bj_gear[k]].x;
+    T.BJ(k, 3) = 0.0;
+  }
+  for (int p = 0; p < nbp; p++) sep[p] = -1.0f;
+  /* control body (kinematic) and the two eye bodies (no shapes) */
+  double4 Pc = G->P[control], Vc = G->V[control], Bc = G->Bv[control];
+  double4 Pe0 = G->P[eye0], Ve0 = G->V[eye0], Be0 = G->Bv[eye0];
+  double4 Pe1 = G->P[eye1], Ve1 = G->V[eye1], Be1 = G->Bv[eye1];
+  double2 Rc = G->R[control], Re0 = G->R[eye0], Re1 = G->R[eye1];
+  /* chain accumulators */
+  double a_pivx, a_pivy, a_gear, a_spr0, a_spr1, a_pin0, a_lim0, a_mot0, a_pin1, a_lim1, a_mot1;
+  { double2 t = G->jacc[jr0]; a_pivx = t.x; a_pivy = t.y; }
+  a_gear = G->jacc[jr0 + 1].x; a_spr0 = G->jacc[jr0 + 2].x; a_spr1 = G->jacc[jr0 + 3].x;
+  a_pin0 = G->jacc[jr0 + 4].x; a_lim0 = G->jacc[jr0 + 5].x; a_mot0 = G->jacc[jr0 + 6].x;
+  a_pin1 = G->jacc[jr0 + 7].x; a_lim1 = G->jacc[jr0 + 8].x; a_mot1 = G->jacc[jr0 + 9].x;
+
+  /* ---- Robot.set_action: id = 9*grip + 3*lr + ud (entities.py:162-186, 439-457) */
+  action = action < 0 ? 0 : (action > 17 ? 17 : action);
+  const int ud = action % 3, lr = (action / 3) % 3, grip = action / 9;
+  const double Rr = sc.robot_radius;
+  double target_speed = 0.0, rel_turn = 0.0;
+  if (ud == 1) target_speed += 4.0 * Rr;
+  if (ud == 2) target_speed -= 3.0 * Rr;
+  if (lr == 1) rel_turn += 1.5;
+  if (lr == 2) rel_turn -= 1.5;
+  const double target_finger = (grip == 0) ? (3.14159265358979323846 / 8) : -0.0;
+  int ncon = 0;
+
+  for (int sub = 0; sub < MG_SUBSTEPS; ++sub) {
+    stamp++;
+    TPE_STAT(0);
+    /* ---- Robot.update (entities.py:459-479) */
+    double rate0, rate1;
+    {
+      Pc.z = T.PR(s_robot, 2) + rel_turn;
+      const double rc = T.PR(s_robot, 3), rs = T.PR(s_robot, 4);
+      Vc.x = rc * 0.0 - rs * target_speed;
+      Vc.y = rc * target_speed + rs * 0.0;
+      const double ra = T.PR(s_robot, 2);
+      {
+        double angle_error = (T.PR(s_f0, 2) - ra) + (-1.0) * target_finger;
+        double r = dmaxf(-1, dminf(1, angle_error * 10));
+        if (fabs(r) < 1e-4) r = 0.0;
+        rate0 = r;
+      }
+      {
+        double angle_error = (T.PR(s_f1, 2) - ra) + (1.0) * target_finger;
+        double r = dmaxf(-1, dminf(1, angle_error * 10));
+        if (fabs(r) < 1e-4) r = 0.0;
+        rate1 = r;
+      }
+    }
+
+    /* ---- integrate positions (cpBodyUpdatePosition; kinematic control body included) */
+    for (int s = 0; s < nslots - 1; s++) {
+      const double vx = T.V(s, 0) + T.Bv(s, 0), vy = T.V(s, 1) + T.Bv(s, 1), vw = T.V(s, 2) + T.Bv(s, 2);
+      const double x = T.PR(s, 0) + vx * dt;
+      const double y = T.PR(s, 1) + vy * dt;
+      const double a = T.PR(s, 2) + vw * dt;
+      double sn, cs;
+      mg_det_sincos(a, &sn, &cs);
+      T.PR(s, 0) = x; T.PR(s, 1) = y; T.PR(s, 2) = a; T.PR(s, 3) = cs; T.PR(s, 4) = sn;
+      T.Bv(s, 0) = 0.0; T.Bv(s, 1) = 0.0; T.Bv(s, 2) = 0.0;
+      /* how far can any point of this body's shapes have moved: |dp|_1 + reach * |dtheta|, rounded up */
+      const double moved = (fabs(vx) + fabs(vy) + TPE_LDG(&ax.body_reach[ax.tpe_slot_body[s]]) * fabs(vw)) * dt;
+      T.path(s) = tpe_fadd_ru(T.path(s), tpe_d2f_ru(moved * 1.000001));
+    }
+#define TPE_INTEGRATE_REG(P, V, B, R)                   \
+  do {                                                  \
+    P.x = P.x + (V.x + B.x) * dt;                       \
+    P.y = P.y + (V.y + B.y) * dt;                       \
+    P.z = P.z + (V.z + B.z) * dt;                       \
+    double sn_, cs_;                                    \
+    mg_det_sincos(P.z, &sn_, &cs_);                     \
+    R = make_double2(cs_, sn_);                         \
+    B = make_double4(0.0, 0.0, 0.0, 0.0);               \
+  } while (0)
+    TPE_INTEGRATE_REG(Pc, Vc, Bc, Rc);
+    TPE_INTEGRATE_REG(Pe0, Ve0, Be0, Re0);
+    TPE_INTEGRATE_REG(Pe1, Ve1, Be1, Re1);
+
+    /* ---- conservative fp32 boxes of the collision groups */
+    for (int g = 0; g < ncg; g++) {
+      const int s0 = sc.cgroups[g].shape0, n = sc.cgroups[g].nshape;
+      float l = INFINITY, b = INFINITY, r = -INFINITY, t = -INFINITY;
+      for (int k = 0; k < n; k++) {
+        const float4 bx = tpe_shape_box(T, ds, s0 + k);
+        l = fminf(l, bx.x); b = fminf(b, bx.y); r = fmaxf(r, bx.z); t = fmaxf(t, bx.w);
+      }
+      T.gbb(g, 0) = l; T.gbb(g, 1) = b; T.gbb(g, 2) = r; T.gbb(g, 3) = t;
+    }
+
+    /* ---- broadphase (own environment): canonical pair list -> the shape pairs that need the exact
+     * narrowphase, as "items" in the private words.  Filters, all exact: group boxes, the cached
+     * separation of the group pair, per-shape boxes for multi-shape groups.  A filtered pair contributes
+     * the gap between its (conservative) boxes to the group pair's separation margin. */
+    int n_items = 0;
+    bool truncated = false;
+    int res_p = 0, res_i = 0, res_k = 0;
+    double res_gm = MG_INF;
+    for (int p = 0; p < nbp && !truncated; p++) {
+      const int ga = sc.bpairs[p][0], gb = sc.bpairs[p][1];
+      const float4 A = make_float4(T.gbb(ga, 0), T.gbb(ga, 1), T.gbb(ga, 2), T.gbb(ga, 3));
+      const float4 B = make_float4(T.gbb(gb, 0), T.gbb(gb, 1), T.gbb(gb, 2), T.gbb(gb, 3));
+      if (!tpe_f4_overlap(A, B)) continue;
+      TPE_STAT(3);
+      const int sla = T.slot(sc.cgroups[ga].body), slb = T.slot(sc.cgroups[gb].body);
+      const float travelled = tpe_fadd_ru(T.path(sla), T.path(slb));
+      if (travelled < sep[p]) { TPE_STAT(4); continue; }
+      const int sa0 = sc.cgroups[ga].shape0, na = sc.cgroups[ga].nshape;
+      const int sb0 = sc.cgroups[gb].shape0, nbs = sc.cgroups[gb].nshape;
+      double gm = MG_INF;
+      const int first_item = n_items;
+      for (int i = 0; i < na && !truncated; i++) {
+        const float4 Ai = (na == 1) ? A : tpe_shape_box(T, ds, sa0 + i);
+        if (na > 1 && !tpe_f4_overlap(Ai, B)) { gm = dminf(gm, tpe_f4_gap(Ai, B)); continue; }
+        for (int k = 0; k < nbs; k++) {
+          if (na > 1 || nbs > 1) {
+            const float4 Bk = (nbs == 1) ? B : tpe_shape_box(T, ds, sb0 + k);
+            if (!tpe_f4_overlap(Ai, Bk)) { gm = dminf(gm, tpe_f4_gap(Ai, Bk)); continue; }
+          }
+          if (n_items == T.L.nitems) { truncated = true; res_p = p; res_i = i; res_k = k; res_gm = gm; break; }
+          int ia = sa0 + i, ib = sb0 + k;
+          if (sc.shapes[ia].kind > sc.shapes[ib].kind) { int t = ia; ia = ib; ib = t; }
+          T.IT(n_items++) = (uint64_t)(uint32_t)(ia | (ib << 8) | (p << 16));
+          TPE_STAT(1);
+        }
+      }
+      if (n_items > first_item) {
+        /* the pair's last item carries the box-filter part of its margin; LAST = settle sep[p] after it,
+         * CONT = the pair continues in the serial tail below */
+        float gmf = gm < 3.0e38 ? tpe_d2f_rd(gm) : 3.0e38f;
+        uint32_t gbits;
+        memcpy(&gbits, &gmf, 4);
+        T.IT(n_items - 1) = (T.IT(n_items - 1) & 0xFFFFFFFFull) | (truncated ? TPE_IT_CONT : TPE_IT_LAST) |
+                            ((uint64_t)gbits << 32);
+      } else if (!truncated) {
+        sep[p] = (gm > 1e-6 && gm < MG_INF) ? tpe_fadd_rd(travelled, tpe_d2f_rd(gm * 0.999999 - 1e-9)) : -1.0f;
+      }
+    }
+
+    /* ---- narrowphase + contact cache lookup (cpCollide + cpArbiterUpdate).
+     * The items of all the warp's environments form one queue; every lane runs the exact narrowphase of
+     * one item (of whichever environment) on the owner's private words, and the owners then pull their
+     * results, in canonical order, with shuffles.  On the host build the "warp" is one lane. */
+    ncon = 0;
+    bool too_many = false;
+    uint32_t cache_used = 0u;
+    const int kcap = T.spill ? TPE_MAX_CONTACTS : T.L.kcon;
+    double gm_run = MG_INF;
+    /* turn one pair's manifold into solver contacts of this environment */
+    auto take_manifold = [&](int ia, int ib, const Manifold& m) {
+      if (m.count == 0) { gm_run = dminf(gm_run, m.margin > 0.0 ? m.margin : 0.0); return; }
+      gm_run = 0.0;
+      TPE_STAT(2);
+      if (ncon + m.count > kcap) { too_many = true; ncon += m.count; return; }
+      int ba = sc.shapes[ia].body, bb = sc.shapes[ib].body;
+      d2 pa = D2(0, 0), pb = D2(0, 0);
+      if (ba >= 0) { const int s = T.slot(ba); pa = D2(T.PR(s, 0), T.PR(s, 1)); } else ba = MG_MAX_BODIES;
+      if (bb >= 0) { const int s = T.slot(bb); pb = D2(T.PR(s, 0), T.PR(s, 1)); } else bb = MG_MAX_BODIES;
+      /* the pair's cached contacts all stem from its last collision; they are warm-started only if
+       * that was the previous sub-step (cpArbiterApplyCachedImpulse skips first-contact arbiters) */
+      bool first = true;
+      double jn[2] = {0.0, 0.0}, jt[2] = {0.0, 0.0};
+      for (int q = 0; q < n_cache; q++) {
+        const CEntry e = G->cache[q];
+        if (e.a == ia && e.b == ib) {
+          if (e.stamp == stamp - 1) first = false;
+          if (m.hash[0] == e.hash) { jn[0] = e.jn; jt[0] = e.jt; }
+          if (m.count > 1 && m.hash[1] == e.hash) { jn[1] = e.jn; jt[1] = e.jt; }
+          cache_used |= 1u << q;
+        }
+      }
+      const double u = sc.shapes[ia].friction * sc.shapes[ib].friction;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (q < m.count) {
+          TpeCon C = tpe_con(T, ncon + q);
+          d2 r1 = dsub(m.p1[q], pa), r2 = dsub(m.p2[q], pb);
+          C[0] = r1.x; C[1] = r1.y; C[2] = r2.x; C[3] = r2.y; C[4] = m.n.x; C[5] = m.n.y;
+          C[9] = jn[q]; C[10] = jt[q]; C[12] = u;
+          C[13] = tpe_pack_ids(m.hash[q], ia, ib, ba, bb, first ? 1 : 0);
+        }
+      }
+      ncon += m.count;
+    };
+    /* shapes `margin` apart cannot touch until the bodies have travelled that far */
+    auto settle_sep = [&](int p, double gm) {
+      const int sla = T.slot(sc.cgroups[sc.bpairs[p][0]].body), slb = T.slot(sc.cgroups[sc.bpairs[p][1]].body);
+      const float travelled = tpe_fadd_ru(T.path(sla), T.path(slb));
+      sep[p] = (gm > 1e-6 && gm < MG_INF) ? tpe_fadd_rd(travelled, tpe_d2f_rd(gm * 0.999999 - 1e-9)) : -1.0f;
+    };
+    {
+      const int lane = tpe_lane<S>();
+      const int incl = tpe_scan_incl<S>(n_items);
+      const int excl = incl - n_items;
+      const int n_all = tpe_shfl<S>(incl, TPE_NL(S) - 1);
+      int consumed = 0;
+      for (int base = 0; base < n_all; base += TPE_NL(S)) {
+        const int j = base + lane;
+        /* owner of queue entry j: the last lane whose exclusive prefix is <= j */
+        int lo = 0, hi = TPE_NL(S) - 1;
+#pragma unroll
+        for (int step = 0; step < 5; step++) {
+          const int mid = (lo + hi + 1) >> 1;
+          const int e = tpe_shfl<S>(excl, mid);
+          if (lo < hi) { if (e <= j) lo = mid; else hi = mid - 1; }
+        }
+        const int owner = lo;
+        const int oexcl = tpe_shfl<S>(excl, owner);
+        Tpe<S> To = T;
+        To.wd = T.wd - lane + owner;
+        To.wf = T.wf - lane + owner;
+        To.slotmap = tpe_shfl64<S>(T.slotmap, owner);
+        To.static_slot = tpe_shfl<S>(T.static_slot, owner);
+        const DeviceScene* dso = (const DeviceScene*)tpe_shfl64<S>((uint64_t)ds, owner);
+        Manifold m;
+        m.count = 0; m.margin = -1.0; m.n = D2(0, 0);
+        m.p1[0] = m.p1[1] = m.p2[0] = m.p2[1] = D2(0, 0);
+        m.hash[0] = m.hash[1] = 0u;
+        if (j < n_all) {
+          const uint32_t it = (uint32_t)To.IT(j - oexcl);
+          tpe_narrow_pair<S>(&To, dso, (int)(it & 0xFFu), (int)((it >> 8) & 0xFFu), &m);
+        }
+        /* owners pull the results of their entries in this round, in order */
+        const int a = (excl > base ? excl : base) - base;
+        const int b = (incl < base + TPE_NL(S) ? incl : base + TPE_NL(S)) - base;
+        const int cnt = b > a ? b - a : 0;
+        const int most = tpe_max<S>(cnt);
+        for (int t = 0; t < most; t++) {
+          const int src = t < cnt ? a + t : lane;
+          Manifold r;
+          r.count = tpe_shfl<S>(m.count, src);
+          r.margin = tpe_shfld<S>(m.margin, src);
+          r.n.x = tpe_shfld<S>(m.n.x, src); r.n.y = tpe_shfld<S>(m.n.y, src);
+          r.p1[0].x = tpe_shfld<S>(m.p1[0].x, src); r.p1[0].y = tpe_shfld<S>(m.p1[0].y, src);
+          r.p2[0].x = tpe_shfld<S>(m.p2[0].x, src); r.p2[0].y = tpe_shfld<S>(m.p2[0].y, src);
+          r.p1[1].x = tpe_shfld<S>(m.p1[1].x, src); r.p1[1].y = tpe_shfld<S>(m.p1[1].y, src);
+          r.p2[1].x = tpe_shfld<S>(m.p2[1].x, src); r.p2[1].y = tpe_shfld<S>(m.p2[1].y, src);
+          r.hash[0] = (unsigned)tpe_shfl<S>((int)m.hash[0], src);
+          r.hash[1] = (unsigned)tpe_shfl<S>((int)m.hash[1], src);
+          if (t < cnt) {
+            const uint64_t itw = T.IT(consumed++);
+            const uint32_t it = (uint32_t)itw;
+            take_manifold((int)(it & 0xFFu), (int)((it >> 8) & 0xFFu), r);
+            if (itw & (TPE_IT_LAST | TPE_IT_CONT)) {
+              float gmf;
+              const uint32_t gbits = (uint32_t)(itw >> 32);
+              memcpy(&gmf, &gbits, 4);
+              const double gm = dminf(gm_run, gmf < 3.0e38f ? (double)gmf : MG_INF);
+              if (itw & TPE_IT_LAST) { settle_sep((int)((it >> 16) & 0xFFu), gm); gm_run = MG_INF; }
+              else gm_run = gm; /* carried into the serial tail */
+            }
+          }
+        }
+      }
+    }
+    if (truncated) {
+      /* serial tail (rare: more candidate pairs than item words): the remaining pairs in canonical order,
+       * without the box filters (the boxes' words now hold contacts) -- tpe_narrow_pair tests the exact
+       * boxes itself */
+      double gm = dminf(gm_run, res_gm);
+      for (int p = res_p; p < nbp; p++) {
+        const int ga = sc.bpairs[p][0], gb = sc.bpairs[p][1];
+        const int sa0 = sc.cgroups[ga].shape0, na = sc.cgroups[ga].nshape;
+        const int sb0 = sc.cgroups[gb].shape0, nbs = sc.cgroups[gb].nshape;
+        if (p != res_p) {
+          const int sla = T.slot(sc.cgroups[ga].body), slb = T.slot(sc.cgroups[gb].body);
+          if (tpe_fadd_ru(T.path(sla), T.path(slb)) < sep[p]) continue;
+          gm = MG_INF;
+        }
+        gm_run = MG_INF;
+        for (int i = (p == res_p ? res_i : 0); i < na; i++)
+          for (int k = (p == res_p && i == res_i ? res_k : 0); k < nbs; k++) {
+            int ia = sa0 + i, ib = sb0 + k;
+            if (sc.shapes[ia].kind > sc.shapes[ib].kind) { int t = ia; ia = ib; ib = t; }
+            Manifold m;
+            tpe_narrow_pair<S>(&T, ds, ia, ib, &m);
+            take_manifold(ia, ib, m);
+          }
+        settle_sep(p, dminf(gm, gm_run));
+      }
+    }
+    if (too_many) {
+      /* capacity exceeded: flag the env and solve this sub-step without contacts rather than with a
+       * partial, order-dependent subset */
+      overflow |= 2;
+      ncon = 0;
+    }
+
+    /* ---- contact prestep */
+    for (int c = 0; c < ncon; c++) {
+      TpeCon C = tpe_con(T, c);
+      const unsigned long long ids = tpe_unpack_ids(C[13]);
+      const int ba = (int)((ids >> 48) & 0x1F), bb = (int)((ids >> 53) & 0x1F);
+      const double ma = ba < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[ba].m_inv) : 0.0;
+      const double ia_ = ba < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[ba].i_inv) : 0.0;
+      const double mb = bb < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[bb].m_inv) : 0.0;
+      const double ib_ = bb < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[bb].i_inv) : 0.0;
+      d2 r1 = D2(C[0], C[1]), r2 = D2(C[2], C[3]), n = D2(C[4], C[5]), t = dperp(n);
+      double rcn1 = dcross(r1, n), rcn2 = dcross(r2, n);
+      C[6] = 1.0 / ((ma + ia_ * rcn1 * rcn1) + (mb + ib_ * rcn2 * rcn2));
+      double rct1 = dcross(r1, t), rct2 = dcross(r2, t);
+      C[7] = 1.0 / ((ma + ia_ * rct1 * rct1) + (mb + ib_ * rct2 * rct2));
+      d2 pa = D2(0, 0), pb = D2(0, 0);
+      if (ba < MG_MAX_BODIES) { const int s = T.slot(ba); pa = D2(T.PR(s, 0), T.PR(s, 1)); }
+      if (bb < MG_MAX_BODIES) { const int s = T.slot(bb); pb = D2(T.PR(s, 0), T.PR(s, 1)); }
+      d2 body_delta = dsub(pb, pa);
+      double dist = ddot(dadd(dsub(r2, r1), body_delta), n);
+      C[8] = -ax.contact_bias_coef * dminf(0.0, dist + MG_COLLISION_SLOP) / dt;
+      C[11] = 0.0;
+    }
+
+    /* ---- joint prestep: chain */
+    const double ang_r = T.PR(s_robot, 2);
+    double b_gear;
+    {
+      const mg_joint_t& J = sc.joints[jr0 + 1];
+      const double maxBias = J.max_bias;
+      b_gear = dclamp(-ax.j_bcoef[jr0 + 1] * (ang_r * J.p1 - Pc.z - J.p0) / dt, -maxBias, maxBias);
+    }
+    TpePin pin0, pin1;
+#define TPE_PIN_PRESTEP(PN, J_, SF)                                                                       \
+  do {                                                                                                    \
+    const mg_joint_t& J = sc.joints[J_];                                                                  \
+    const double rac = T.PR(s_robot, 3), ras = T.PR(s_robot, 4), rbc = T.PR(SF, 3), rbs = T.PR(SF, 4);    \
+    d2 r1 = D2(rac * J.anchor_a[0] - ras * J.anchor_a[1], ras * J.anchor_a[0] + rac * J.anchor_a[1]);     \
+    d2 r2 = D2(rbc * J.anchor_b[0] - rbs * J.anchor_b[1], rbs * J.anchor_b[0] + rbc * J.anchor_b[1]);     \
+    d2 pa = D2(T.PR(s_robot, 0), T.PR(s_robot, 1)), pb = D2(T.PR(SF, 0), T.PR(SF, 1));                    \
+    d2 delta = dsub(dadd(pb, r2), dadd(pa, r1));                                                          \
+    double dist = dlength(delta);                                                                         \
+    d2 n = dmul(delta, 1.0 / (dist ? dist : MG_INF));                                                     \
+    const TpeJC c = tpe_jc(ds, J_);                                                                       \
+    double rcn1 = dcross(r1, n), rcn2 = dcross(r2, n);                                                    \
+    double k = (c.ma + c.ia * rcn1 * rcn1) + (c.mb + c.ib * rcn2 * rcn2);                                 \
+    const double maxBias = J.max_bias;                                                                    \
+    PN.r1x = r1.x; PN.r1y = r1.y; PN.r2x = r2.x; PN.r2y = r2.y; PN.nx = n.x; PN.ny = n.y;                 \
+    PN.nMass = 1.0 / k;                                                                                   \
+    PN.bias = dclamp(-ax.j_bcoef[J_] * (dist - J.p0) / dt, -maxBias, maxBias);                            \
+  } while (0)
+    TPE_PIN_PRESTEP(pin0, jr0 + 4, s_f0);
+    TPE_PIN_PRESTEP(pin1, jr0 + 7, s_f1);
+    double b_lim0, b_lim1;
+#define TPE_LIMIT_PRESTEP(B_, ACC, J_, SF)                                     \
+  do {                                                                         \
+    const mg_joint_t& J = sc.joints[J_];                                       \
+    double dist = T.PR(SF, 2) - ang_r;                                         \
+    double pdist = 0.0;                                                        \
+    if (dist > J.p1) pdist = J.p1 - dist;                                      \
+    else if (dist < J.p0) pdist = J.p0 - dist;                                 \
+    const double maxBias = J.max_bias;                                         \
+    B_ = dclamp(-ax.j_bcoef[J_] * pdist / dt, -maxBias, maxBias);              \
+    if (!B_) ACC = 0.0;                                                        \
+  } while (0)
+    TPE_LIMIT_PRESTEP(b_lim0, a_lim0, jr0 + 5, s_f0);
+    TPE_LIMIT_PRESTEP(b_lim1, a_lim1, jr0 + 8, s_f1);
+    /* blocks' gear bias (drag joints against the static body) */
+    for (int k = 0; k < nblk; k++) {
+      const int jg = ax.tpe_bj_gear[k];
+      const mg_joint_t& J = sc.joints[jg];
+      const double maxBias = J.max_bias;
+      const double ang_b = T.PR(ax.tpe_bj_slot[k], 2);
+      T.BJ(k, 3) = dclamp(-ax.j_bcoef[jg] * (ang_b * J.p1 - 0.0 - J.p0) / dt, -maxBias, maxBias);
+    }
+
+    /* chain velocities live in registers while joints run */
+    double rvx = T.V(s_robot, 0), rvy = T.V(s_robot, 1), rw = T.V(s_robot, 2);
+    double f0x = T.V(s_f0, 0), f0y = T.V(s_f0, 1), f0w = T.V(s_f0, 2);
+    double f1x = T.V(s_f1, 0), f1y = T.V(s_f1, 1), f1w = T.V(s_f1, 2);
+    double e0w = Ve0.z, e1w = Ve1.z;
+    const TpeJC c_piv = tpe_jc(ds, jr0), c_gear = tpe_jc(ds, jr0 + 1), c_sp0 = tpe_jc(ds, jr0 + 2),
+                c_sp1 = tpe_jc(ds, jr0 + 3), c_pin0 = tpe_jc(ds, jr0 + 4), c_lim0 = tpe_jc(ds, jr0 + 5),
+                c_mot0 = tpe_jc(ds, jr0 + 6), c_pin1 = tpe_jc(ds, jr0 + 7), c_lim1 = tpe_jc(ds, jr0 + 8),
+                c_mot1 = tpe_jc(ds, jr0 + 9);
+    /* rotary springs: their preStep applies the spring impulse, sequentially in insertion order */
+    double t_spr0 = 0.0, t_spr1 = 0.0;
+    {
+      const mg_joint_t& J = sc.joints[jr0 + 2];
+      double j_spring = ((ang_r - Pe0.z) - J.p0) * J.p1 * MG_DT;
+      a_spr0 = j_spring;
+      rw -= j_spring * c_sp0.ia;
+      e0w += j_spring * c_sp0.ib;
+    }
+    {
+      const mg_joint_t& J = sc.joints[jr0 + 3];
+      double j_spring = ((ang_r - Pe1.z) - J.p0) * J.p1 * MG_DT;
+      a_spr1 = j_spring;
+      rw -= j_spring * c_sp1.ia;
+      e1w += j_spring * c_sp1.ib;
+    }
+    T.V(s_robot, 2) = rw;
+
+    /* ---- warm start (cpArbiterApplyCachedImpulse, then the joints' applyCachedImpulse; dt_coef = 1) */
+    for (int c = 0; c < ncon; c++) {
+      TpeCon C = tpe_con(T, c);
+      const unsigned long long ids = tpe_unpack_ids(C[13]);
+      if ((ids >> 58) & 1ull) continue; /* first contact of the pair */
+      const int ba = (int)((ids >> 48) & 0x1F), bb = (int)((ids >> 53) & 0x1F);
+      const int sa_ = T.slot(ba), sb_ = T.slot(bb);
+      const double ma = ba < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[ba].m_inv) : 0.0;
+      const double ia_ = ba < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[ba].i_inv) : 0.0;
+      const double mb = bb < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[bb].m_inv) : 0.0;
+      const double ib_ = bb < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[bb].i_inv) : 0.0;
+      const double nx = C[4], ny = C[5], cjn = C[9], cjt = C[10];
+      const double jx = nx * cjn - ny * cjt, jy = nx * cjt + ny * cjn;
+      TPE_APPLY(V, sa_, ma, ia_, -jx, -jy, C[0], C[1]);
+      TPE_APPLY(V, sb_, mb, ib_, jx, jy, C[2], C[3]);
+    }
+    rvx = T.V(s_robot, 0); rvy = T.V(s_robot, 1); rw = T.V(s_robot, 2);
+    f0x = T.V(s_f0, 0); f0y = T.V(s_f0, 1); f0w = T.V(s_f0, 2);
+    f1x = T.V(s_f1, 0); f1y = T.V(s_f1, 1); f1w = T.V(s_f1, 2);
+    {
+      /* pivot (control -> robot): anchors at the body origins, no angular part */
+      rvx = rvx + a_pivx * c_piv.mb; rvy = rvy + a_pivy * c_piv.mb;
+      /* gear (control -> robot) */
+      rw += a_gear * c_gear.ib;
+      /* springs: nothing cached; pins, limits, motors of the two fingers */
+#define TPE_PIN_WARM(PN, C_, ACC, FX, FY, FW)                      \
+  do {                                                             \
+    double jx = PN.nx * ACC, jy = PN.ny * ACC;                     \
+    rvx = rvx + (-jx) * C_.ma; rvy = rvy + (-jy) * C_.ma;          \
+    rw += C_.ia * (PN.r1x * (-jy) - PN.r1y * (-jx));               \
+    FX = FX + jx * C_.mb; FY = FY + jy * C_.mb;                    \
+    FW += C_.ib * (PN.r2x * jy - PN.r2y * jx);                     \
+  } while (0)
+#define TPE_ANG_WARM(C_, ACC, FW)   \
+  do {                              \
+    double da = ACC * C_.ia;        \
+    rw -= da;                       \
+    FW += ACC * C_.ib;              \
+  } while (0)
+      TPE_PIN_WARM(pin0, c_pin0, a_pin0, f0x, f0y, f0w);
+      TPE_ANG_WARM(c_lim0, a_lim0, f0w);
+      TPE_ANG_WARM(c_mot0, a_mot0, f0w);
+      TPE_PIN_WARM(pin1, c_pin1, a_pin1, f1x, f1y, f1w);
+      TPE_ANG_WARM(c_lim1, a_lim1, f1w);
+      TPE_ANG_WARM(c_mot1, a_mot1, f1w);
+    }
+    for (int k = 0; k < nblk; k++) {
+      const int s = ax.tpe_bj_slot[k];
+      const TpeJC cp = tpe_jc(ds, ax.tpe_bj_pivot[k]), cg = tpe_jc(ds, ax.tpe_bj_gear[k]);
+      T.V(s, 0) = T.V(s, 0) + T.BJ(k, 0) * cp.mb;
+      T.V(s, 1) = T.V(s, 1) + T.BJ(k, 1) * cp.mb;
+      T.V(s, 2) += T.BJ(k, 2) * cg.ib;
+    }
+    T.V(s_robot, 0) = rvx; T.V(s_robot, 1) = rvy; T.V(s_robot, 2) = rw;
+    T.V(s_f0, 0) = f0x; T.V(s_f0, 1) = f0y; T.V(s_f0, 2) = f0w;
+    T.V(s_f1, 0) = f1x; T.V(s_f1, 1) = f1y; T.V(s_f1, 2) = f1w;
+
+    /* ---- solver iterations (cpArbiterApplyImpulse for every arbiter, then every joint) */
+    for (int it = 0; it < MG_ITERATIONS; ++it) {
+      for (int c = 0; c < ncon; c++) {
+        TpeCon C = tpe_con(T, c);
+        const unsigned long long ids = tpe_unpack_ids(C[13]);
+        const int ba = (int)((ids >> 48) & 0x1F), bb = (int)((ids >> 53) & 0x1F);
+        const int sa_ = T.slot(ba), sb_ = T.slot(bb);
+        const double c_ma = ba < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[ba].m_inv) : 0.0;
+        const double c_ia = ba < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[ba].i_inv) : 0.0;
+        const double c_mb = bb < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[bb].m_inv) : 0.0;
+        const double c_ib = bb < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[bb].i_inv) : 0.0;
+        const double c_r1x = C[0], c_r1y = C[1], c_r2x = C[2], c_r2y = C[3], c_nx = C[4], c_ny = C[5];
+        const double c_nMass = C[6], c_tMass = C[7], c_bias = C[8], c_u = C[12];
+        double c_jn = C[9], c_jt = C[10], c_jb = C[11];
+        const double vax = T.V(sa_, 0), vay = T.V(sa_, 1), vaz = T.V(sa_, 2);
+        const double vbx = T.V(sb_, 0), vby = T.V(sb_, 1), vbz = T.V(sb_, 2);
+        const double bax = T.Bv(sa_, 0), bay = T.Bv(sa_, 1), baz = T.Bv(sa_, 2);
+        const double bbx = T.Bv(sb_, 0), bby = T.Bv(sb_, 1), bbz = T.Bv(sb_, 2);
+        /* vb1 = a.v_bias + perp(r1)*a.w_bias, etc. */
+        double vb1x = bax + (-c_r1y) * baz, vb1y = bay + c_r1x * baz;
+        double vb2x = bbx + (-c_r2y) * bbz, vb2y = bby + c_r2x * bbz;
+        double v1x = vax + (-c_r1y) * vaz, v1y = vay + c_r1x * vaz;
+        double v2x = vbx + (-c_r2y) * vbz, v2y = vby + c_r2x * vbz;
+        double vrx = v2x - v1x, vry = v2y - v1y;
+        double vbn = (vb2x - vb1x) * c_nx + (vb2y - vb1y) * c_ny;
+        double vrn = vrx * c_nx + vry * c_ny;
+        double vrt = vrx * (-c_ny) + vry * c_nx;
+        double jbn = (c_bias - vbn) * c_nMass;
+        double jbnOld = c_jb;
+        c_jb = dmaxf(jbnOld + jbn, 0.0);
+        double jn = -(0.0 + vrn) * c_nMass;
+        double jnOld = c_jn;
+        c_jn = dmaxf(jnOld + jn, 0.0);
+        double jtMax = c_u * c_jn;
+        double jt = -vrt * c_tMass;
+        double jtOld = c_jt;
+        c_jt = dclamp(jtOld + jt, -jtMax, jtMax);
+        double bjx = c_nx * (c_jb - jbnOld), bjy = c_ny * (c_jb - jbnOld);
+        TPE_APPLY(Bv, sa_, c_ma, c_ia, -bjx, -bjy, c_r1x, c_r1y);
+        TPE_APPLY(Bv, sb_, c_mb, c_ib, bjx, bjy, c_r2x, c_r2y);
+        double dn = c_jn - jnOld, dtt = c_jt - jtOld;
+        double jx = c_nx * dn - c_ny * dtt, jy = c_nx * dtt + c_ny * dn;
+        TPE_APPLY(V, sa_, c_ma, c_ia, -jx, -jy, c_r1x, c_r1y);
+        TPE_APPLY(V, sb_, c_mb, c_ib, jx, jy, c_r2x, c_r2y);
+        C[9] = c_jn; C[10] = c_jt; C[11] = c_jb;
+      }
+      /* blocks: force-capped pivot + gear against the static body (entities.py:703-711) */
+      for (int k = 0; k < nblk; k++) {
+        const int s = ax.tpe_bj_slot[k];
+        const TpeJC cp = tpe_jc(ds, ax.tpe_bj_pivot[k]), cg = tpe_jc(ds, ax.tpe_bj_gear[k]);
+        double vbx = T.V(s, 0), vby = T.V(s, 1), wb = T.V(s, 2);
+        {
+          double jx = (0.0 - (vbx - 0.0)) * cp.c0;
+          double jy = (0.0 - (vby - 0.0)) * cp.c0;
+          const double ox = T.BJ(k, 0), oy = T.BJ(k, 1);
+          d2 acc = dvclamp(D2(ox + jx, oy + jy), cp.c1);
+          T.BJ(k, 0) = acc.x; T.BJ(k, 1) = acc.y;
+          jx = acc.x - ox; jy = acc.y - oy;
+          vbx = vbx + jx * cp.mb; vby = vby + jy * cp.mb;
+        }
+        {
+          double acc = T.BJ(k, 2), wa = 0.0;
+          tpe_gear(cg, T.BJ(k, 3), acc, wa, wb);
+          T.BJ(k, 2) = acc;
+        }
+        T.V(s, 0) = vbx; T.V(s, 1) = vby; T.V(s, 2) = wb;
+      }
+      /* the robot chain, in insertion order (entities.py:255-354) */
+      rvx = T.V(s_robot, 0); rvy = T.V(s_robot, 1); rw = T.V(s_robot, 2);
+      f0x = T.V(s_f0, 0); f0y = T.V(s_f0, 1); f0w = T.V(s_f0, 2);
+      f1x = T.V(s_f1, 0); f1y = T.V(s_f1, 1); f1w = T.V(s_f1, 2);
+      {
+        double jx = (0.0 - (rvx - Vc.x)) * c_piv.c0;
+        double jy = (0.0 - (rvy - Vc.y)) * c_piv.c0;
+        const double ox = a_pivx, oy = a_pivy;
+        d2 acc = dvclamp(D2(ox + jx, oy + jy), c_piv.c1);
+        a_pivx = acc.x; a_pivy = acc.y;
+        jx = acc.x - ox; jy = acc.y - oy;
+        rvx = rvx + jx * c_piv.mb; rvy = rvy + jy * c_piv.mb;
+      }
+      {
+        double wa = Vc.z;
+        tpe_gear(c_gear, b_gear, a_gear, wa, rw);
+      }
+      tpe_spring(c_sp0, t_spr0, a_spr0, rw, e0w);
+      tpe_spring(c_sp1, t_spr1, a_spr1, rw, e1w);
+      tpe_pin(c_pin0, pin0, a_pin0, rvx, rvy, rw, f0x, f0y, f0w);
+      tpe_limit(c_lim0, b_lim0, a_lim0, rw, f0w);
+      tpe_motor(c_mot0, rate0, a_mot0, rw, f0w);
+      tpe_pin(c_pin1, pin1, a_pin1, rvx, rvy, rw, f1x, f1y, f1w);
+      tpe_limit(c_lim1, b_lim1, a_lim1, rw, f1w);
+      tpe_motor(c_mot1, rate1, a_mot1, rw, f1w);
+      T.V(s_robot, 0) = rvx; T.V(s_robot, 1) = rvy; T.V(s_robot, 2) = rw;
+      T.V(s_f0, 0) = f0x; T.V(s_f0, 1) = f0y; T.V(s_f0, 2) = f0w;
+      T.V(s_f1, 0) = f1x; T.V(s_f1, 1) = f1y; T.V(s_f1, 2) = f1w;
+    }
+    Ve0.z = e0w; Ve1.z = e1w;
+
+    /* ---- rebuild the contact cache: this sub-step's contacts first (canonical order), then the entries
+     * of pairs that did not collide now and are younger than the persistence window
+     * (cpSpaceArbiterSetFilter), in their old order */
+    if (n_cache > 0 || ncon > 0) {
+      int nsurv = 0;
+      for (int q = 0; q < n_cache; q++) { /* compact the survivors in place (their rank never exceeds q) */
+        const CEntry e = G->cache[q];
+        if (((cache_used >> q) & 1u) == 0 && (stamp - e.stamp) < MG_PERSISTENCE) {
+          if (nsurv != q) G->cache[nsurv] = e;
+          nsurv++;
+        }
+      }
+      int tot = ncon + nsurv;
+      if (tot > MG_NCACHE) { tot = MG_NCACHE; overflow |= 4; }
+      if (ncon > 0)
+        for (int q = tot - ncon - 1; q >= 0; q--) G->cache[q + ncon] = G->cache[q]; /* shift up, back to front */
+      for (int c = 0; c < ncon; c++) {
+        TpeCon C = tpe_con(T, c);
+        const unsigned long long ids = tpe_unpack_ids(C[13]);
+        CEntry e;
+        e.a = (uint8_t)((ids >> 32) & 0xFF); e.b = (uint8_t)((ids >> 40) & 0xFF); e.used = 0; e.pad_ = 0;
+        e.hash = (uint32_t)(ids & 0xFFFFFFFFull); e.stamp = stamp; e.pad2_ = 0;
+        e.jn = C[9]; e.jt = C[10];
+        G->cache[c] = e;
+      }
+      n_cache = tot;
+    }
+  }
+
+  /* ---- store the record */
+  if (!live) return;
+  for (int s = 0; s < nslots - 1; s++) {
+    const int b = ax.tpe_slot_body[s];
+    G->V[b] = make_double4(T.V(s, 0), T.V(s, 1), T.V(s, 2), 0.0);
+    G->Bv[b] = make_double4(T.Bv(s, 0), T.Bv(s, 1), T.Bv(s, 2), 0.0);
+    G->P[b] = make_double4(T.PR(s, 0), T.PR(s, 1), T.PR(s, 2), 0.0);
+    G->R[b] = make_double2(T.PR(s, 3), T.PR(s, 4));
+  }
+  G->P[control] = Pc; G->V[control] = Vc; G->Bv[control] = Bc; G->R[control] = Rc;
+  G->P[eye0] = Pe0; G->V[eye0] = Ve0; G->Bv[eye0] = Be0; G->R[eye0] = Re0;
+  G->P[eye1] = Pe1; G->V[eye1] = Ve1; G->Bv[eye1] = Be1; G->R[eye1] = Re1;
+  for (int k = 0; k < nblk; k++) {
+    G->jacc[ax.tpe_bj_pivot[k]] = make_double2(T.BJ(k, 0), T.BJ(k, 1));
+    G->jacc[ax.tpe_bj_gear[k]].x = T.BJ(k, 2);
+  }
+  G->jacc[jr0] = make_double2(a_pivx, a_pivy);
+  G->jacc[jr0 + 1].x = a_gear; G->jacc[jr0 + 2].x = a_spr0; G->jacc[jr0 + 3].x = a_spr1;
+  G->jacc[jr0 + 4].x = a_pin0; G->jacc[jr0 + 5].x = a_lim0; G->jacc[jr0 + 6].x = a_mot0;
+  G->jacc[jr0 + 7].x = a_pin1; G->jacc[jr0 + 8].x = a_lim1; G->jacc[jr0 + 9].x = a_mot1;
+  G->stamp = stamp;
+  G->n_cache = n_cache;
+  G->overflow = overflow;
+  G->last_contacts = ncon;
+}
+
+#endif /* MG_PHYSICS_TPE_H */

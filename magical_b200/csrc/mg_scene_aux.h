@@ -22,6 +22,7 @@
 #define MG_ITERATIONS 10         /* benchmarks/__init__.py:404 */
 #define MG_COLLISION_SLOP 0.01   /* base_env.py:195 */
 #define MG_MAX_LEVELS 32
+#define TPE_NO_SLOT_ 15
 
 typedef struct {
   double cnorm[MG_MAX_CVERTS][2]; /* poly: plane i = edge (v[i-1] -> v[i]); segment: normal at vert0 */
@@ -47,6 +48,17 @@ typedef struct {
   uint32_t jpack[MG_MAX_JOINTS]; /* kind | a << 8 | b << 16 | pin slot << 24 */
   int32_t max_per_level;        /* lanes the joint schedule needs (must fit the lanes that serve one environment) */
   int32_t pad2_;
+  /* thread-per-environment kernel (mg_physics_tpe.h): the scene must have MAGICAL's canonical structure --
+   * one robot whose ten joints appear consecutively in the order of entities.py:255-354, and blocks that each
+   * carry exactly a pivot + gear drag pair against the static body (entities.py:703-711) */
+  int32_t tpe_ok;
+  int32_t tpe_nslots;           /* velocity slots: bodies owning collision shapes + the static dummy (last) */
+  int32_t tpe_nblocks;
+  int32_t tpe_jr0;              /* first robot joint: jr0+0 pivot, +1 gear, +2,+3 springs, +4..6 / +7..9 pin, limit, motor */
+  uint64_t tpe_slotmap;         /* nibble b = slot of body b, 15 = the body has no slot (control, eyes) */
+  uint8_t tpe_slot_body[16];    /* slot -> body */
+  uint8_t tpe_bj_pivot[MG_MAX_BLOCKS], tpe_bj_gear[MG_MAX_BLOCKS], tpe_bj_slot[MG_MAX_BLOCKS];
+  uint8_t tpe_pad_[2];
   int32_t ok;                       /* 0 if the scene uses a feature the kernels do not implement */
   int32_t pad_;
 } mg_scene_aux_t;
@@ -58,6 +70,80 @@ static inline void mg_aux_norm(double ax, double ay, double bx, double by, doubl
   double inv = 1.0 / (sqrt(rx * rx + ry * ry) + 2.2250738585072014e-308);
   *nx = rx * inv;
   *ny = ry * inv;
+}
+
+/* Recognise the canonical MAGICAL structure for the thread-per-environment kernel; sets aux->tpe_ok. */
+static inline void mg_build_tpe_aux(const mg_scene_t* s, mg_scene_aux_t* aux) {
+  aux->tpe_ok = 0;
+  const int robot = s->robot_body, control = s->control_body;
+  if (robot < 0 || robot >= s->n_bodies || control < 0 || control >= s->n_bodies) return;
+  if (s->bodies[control].kind != MG_BODY_KINEMATIC) return;
+  /* bodies that own collision shapes */
+  int shaped[MG_MAX_BODIES];
+  for (int b = 0; b < MG_MAX_BODIES; b++) shaped[b] = 0;
+  for (int i = 0; i < s->n_shapes; i++)
+    if (s->shapes[i].body >= 0) shaped[s->shapes[i].body] = 1;
+  for (int g = 0; g < s->n_cgroups; g++) { /* a group's shapes all sit on the group's body */
+    for (int k = 0; k < s->cgroups[g].nshape; k++)
+      if (s->shapes[s->cgroups[g].shape0 + k].body != s->cgroups[g].body) return;
+  }
+  if (shaped[control] || shaped[s->eye_body[0]] || shaped[s->eye_body[1]]) return;
+  if (!shaped[robot] || !shaped[s->finger_body[0]] || !shaped[s->finger_body[1]]) return;
+  /* robot chain */
+  int jr0 = -1;
+  for (int j = 0; j < s->n_joints; j++)
+    if (s->joints[j].kind == MG_JOINT_PIVOT && s->joints[j].a == control && s->joints[j].b == robot) { jr0 = j; break; }
+  if (jr0 < 0 || jr0 + 10 > s->n_joints) return;
+  const int kinds[10] = {MG_JOINT_PIVOT, MG_JOINT_GEAR, MG_JOINT_ROTARY_SPRING, MG_JOINT_ROTARY_SPRING, MG_JOINT_PIN,
+                         MG_JOINT_ROTARY_LIMIT, MG_JOINT_MOTOR, MG_JOINT_PIN, MG_JOINT_ROTARY_LIMIT, MG_JOINT_MOTOR};
+  const int ja[10] = {control, control, robot, robot, robot, robot, robot, robot, robot, robot};
+  const int jb[10] = {robot, robot, s->eye_body[0], s->eye_body[1], s->finger_body[0], s->finger_body[0],
+                      s->finger_body[0], s->finger_body[1], s->finger_body[1], s->finger_body[1]};
+  for (int k = 0; k < 10; k++) {
+    const mg_joint_t* jt = &s->joints[jr0 + k];
+    if (jt->kind != kinds[k] || jt->a != ja[k] || jt->b != jb[k]) return;
+  }
+  if (s->motor_joint[0] != jr0 + 6 || s->motor_joint[1] != jr0 + 9) return;
+  if (s->joints[jr0 + 1].p1 == 0.0) return;
+  /* every other joint: (pivot, gear) pairs static -> body */
+  int nblk = 0;
+  int used_body[MG_MAX_BODIES];
+  for (int b = 0; b < MG_MAX_BODIES; b++) used_body[b] = 0;
+  for (int j = 0; j < s->n_joints;) {
+    if (j == jr0) { j += 10; continue; }
+    if (j + 1 >= s->n_joints) return;
+    const mg_joint_t *p = &s->joints[j], *g = &s->joints[j + 1];
+    if (p->kind != MG_JOINT_PIVOT || g->kind != MG_JOINT_GEAR || p->a >= 0 || g->a >= 0 || p->b != g->b) return;
+    if (p->b < 0 || p->b >= s->n_bodies || !shaped[p->b] || used_body[p->b] || nblk >= MG_MAX_BLOCKS) return;
+    if (p->b == robot || p->b == s->finger_body[0] || p->b == s->finger_body[1]) return;
+    if (s->bodies[p->b].kind != MG_BODY_DYNAMIC || g->p1 == 0.0) return;
+    used_body[p->b] = 1;
+    aux->tpe_bj_pivot[nblk] = (uint8_t)j;
+    aux->tpe_bj_gear[nblk] = (uint8_t)(j + 1);
+    aux->tpe_bj_slot[nblk] = (uint8_t)p->b; /* body for now, mapped to its slot below */
+    nblk++;
+    j += 2;
+  }
+  /* slots: shaped bodies in body order; every shaped body must be the robot, a finger or a jointed block */
+  int nslots = 0;
+  uint64_t map = 0;
+  for (int b = 0; b < MG_MAX_BODIES; b++) {
+    int slot = TPE_NO_SLOT_;
+    if (b < s->n_bodies && shaped[b]) {
+      if (!(b == robot || b == s->finger_body[0] || b == s->finger_body[1] || used_body[b])) return;
+      if (s->bodies[b].kind != MG_BODY_DYNAMIC) return;
+      slot = nslots;
+      aux->tpe_slot_body[nslots++] = (uint8_t)b;
+    }
+    map |= (uint64_t)slot << (4 * b);
+  }
+  if (nslots + 1 > 15) return;
+  for (int k = 0; k < nblk; k++) aux->tpe_bj_slot[k] = (uint8_t)((map >> (4 * aux->tpe_bj_slot[k])) & 15u);
+  aux->tpe_slotmap = map;
+  aux->tpe_nslots = nslots + 1;
+  aux->tpe_nblocks = nblk;
+  aux->tpe_jr0 = jr0;
+  aux->tpe_ok = 1;
 }
 
 static inline const char* mg_build_scene_aux(const mg_scene_t* s, mg_scene_aux_t* aux) {
@@ -225,6 +311,7 @@ static inline const char* mg_build_scene_aux(const mg_scene_t* s, mg_scene_aux_t
   }
   aux->contact_bias_coef = 1.0 - pow(pow(1.0 - 0.1, 60.0), dt);
   aux->ok = 1;
+  mg_build_tpe_aux(s, aux);
   return 0;
 }
 

@@ -1,0 +1,82 @@
+"""ctypes binding of tests/host/libtpe_host.so: the PRODUCT's thread-per-env
+physics step (magical_b200/csrc/mg_physics_tpe.h) compiled for the host, so
+CPU tests can check the kernel's own source against the oracle."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from magical_b200 import scene as sc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'host', 'tpe_host.cpp')
+LIB = os.path.join(HERE, 'host', 'libtpe_host.so')
+CUDA_INC = os.environ.get('CUDA_INC', '/usr/local/cuda/include')
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        root = os.path.dirname(HERE)
+        csrc = os.path.join(root, 'magical_b200', 'csrc')
+        deps = [SRC, os.path.join(root, 'include', 'magical_b200.h')] + [
+            os.path.join(csrc, f) for f in os.listdir(csrc)
+            if f.endswith(('.h', '.cuh'))]
+        if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(
+                map(os.path.getmtime, deps)):
+            subprocess.run(['g++', '-O2', '-fPIC', '-shared', '-std=c++17',
+                            '-ffp-contract=off', '-I', CUDA_INC, '-o', LIB,
+                            SRC, '-lm'], check=True)
+        L = ctypes.CDLL(LIB)
+        vp, i32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+        L.tpeh_create.restype = vp
+        L.tpeh_create.argtypes = [vp, i32, i32, i32]
+        L.tpeh_destroy.argtypes = [vp]
+        L.tpeh_reset.argtypes = [vp]
+        L.tpeh_step.argtypes = [vp, i32]
+        L.tpeh_get_state.argtypes = [vp, vp]
+        L.tpeh_set_pose.argtypes = [vp, i32, f64, f64, f64]
+        L.tpeh_kcon.argtypes = [vp]
+        L.tpeh_words.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+class TpeHostEnv:
+    def __init__(self, scene_record, kcon=8, spill=True, nitems=12):
+        self._lib = lib()
+        self._scene = np.ascontiguousarray(scene_record).copy()
+        self._h = self._lib.tpeh_create(self._scene.ctypes.data, kcon,
+                                        int(spill), nitems)
+        assert self._h, 'scene rejected by the thread-per-env path'
+
+    @property
+    def kcon(self):
+        return self._lib.tpeh_kcon(self._h)
+
+    @property
+    def words(self):
+        return self._lib.tpeh_words(self._h)
+
+    def step(self, action):
+        self._lib.tpeh_step(self._h, int(action))
+
+    def reset(self):
+        self._lib.tpeh_reset(self._h)
+
+    def set_pose(self, body, x, y, angle):
+        self._lib.tpeh_set_pose(self._h, body, x, y, angle)
+
+    def state(self):
+        st = np.zeros((), dtype=sc.state_dt)
+        self._lib.tpeh_get_state(self._h, st.ctypes.data)
+        return st
+
+    def close(self):
+        if self._h:
+            self._lib.tpeh_destroy(self._h)
+            self._h = None
+
+    __del__ = close
