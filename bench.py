@@ -228,6 +228,19 @@ def run_b200(args, env_id, batch):
                                 dtype=torch.uint8, device=dev)
                 dist.all_gather_into_tensor(g, venv.obs)
 
+    # ---- prelude (untimed): spread the episode phases uniformly over the batch.  All envs start at
+    # step 0 with the blocks apart; contact load grows over an episode, so timing the first steps of
+    # synchronised episodes would flatter the physics.  One episode's worth of steps, resetting
+    # 1/max_steps of the envs after each, leaves env i at phase (i mod max_steps): the steady-state mix
+    # of a long auto-resetting rollout.
+    prelude = venv.max_episode_steps if args.prelude < 0 else args.prelude
+    if prelude > 0:
+        ids = np.arange(batch)
+        for t in range(prelude):
+            venv.step(act_pool[t % n_pool])
+            sel = ids[ids % prelude == t]
+            if len(sel):
+                venv.reset(env_ids=sel)
     # ---- value: device-resident actions
     for i in range(W):
         obs, rew, done, info = venv.step(act_pool[i % n_pool])
@@ -325,6 +338,8 @@ def run_b200(args, env_id, batch):
             'env_id': env_id, 'batch_per_gpu': batch, 'global_batch': batch * world,
             'parallelism': f'env-sharded dp{world}; all-gather of reward/done/score'
                            + (' + obs' if args.gather_obs else ''),
+            'episode_phase': (f'uniform over the {prelude}-step episode (untimed prelude of {prelude} steps '
+                              'with staggered resets)') if prelude > 0 else 'all envs at episode start',
             'l2': 'state (229 MB) + obs (7.2 GB) per step exceed the 126 MB L2'
                   if batch >= 65536 else 'inputs smaller than L2 (small-batch config)',
         },
@@ -357,6 +372,8 @@ def main():
     ap.add_argument('--workload', default='cluster65536', choices=list(WORKLOADS))
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--gather-obs', action='store_true')
+    ap.add_argument('--prelude', type=int, default=-1,
+                    help='untimed steps that stagger the episode phases (-1: one episode, 0: none)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

@@ -188,26 +188,27 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   /* K1 variant: every MAGICAL scene has the canonical robot + drag-jointed blocks structure and runs one
    * environment per thread; anything else (hand-built scenes) falls back to the cooperative kernel */
   h->use_tpe = 1;
-  int max_slots = 0, max_blocks = 0, max_groups = 0;
+  int max_slots = 0, max_blocks = 0, max_groups = 0, max_pairs = 0;
   for (int i = 0; i < cfg->n_scenes; i++) {
     if (!host[i].aux.tpe_ok) h->use_tpe = 0;
     if (host[i].aux.tpe_nslots > max_slots) max_slots = host[i].aux.tpe_nslots;
     if (host[i].aux.tpe_nblocks > max_blocks) max_blocks = host[i].aux.tpe_nblocks;
     if (scenes[i].n_cgroups > max_groups) max_groups = scenes[i].n_cgroups;
+    if (scenes[i].n_bpairs > max_pairs) max_pairs = scenes[i].n_bpairs;
   }
   if (const char* ev = getenv("MG_PHYSICS")) {
     if (!strcmp(ev, "warp")) h->use_tpe = 0;
   }
   if (h->use_tpe) {
-    int kcon = 6;
+    int kcon = 5;
     if (const char* ev = getenv("MG_TPE_KCON")) kcon = atoi(ev);
     if (kcon < 1) kcon = 1;
     if (kcon > TPE_MAX_CONTACTS) kcon = TPE_MAX_CONTACTS;
-    int nitems = 12;
+    int nitems = 48;
     if (const char* ev = getenv("MG_TPE_NITEMS")) nitems = atoi(ev);
-    h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, kcon, nitems);
+    h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, max_pairs, kcon, nitems);
     while (mg_tpe_smem_bytes(&h->tpe) > 200 * 1024 && kcon > 1)
-      h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, --kcon, nitems);
+      h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, max_pairs, --kcon, nitems);
   }
   cudaError_t e;
   if ((e = cudaMalloc(&h->d_states, sizeof(EnvState) * (size_t)cfg->batch)) != cudaSuccess ||

@@ -27,7 +27,13 @@
 
 #if defined(__CUDACC__)
 #define MG_HD __host__ __device__ __forceinline__
+#if defined(MG_NP_FORCE_INLINE)
+/* GJK / EPA inlined into their (single, itself out-of-line) caller: the shape views then live in
+ * registers instead of being read through references from local memory at every vertex access */
+#define MG_HD_NOINLINE __host__ __device__ __forceinline__
+#else
 #define MG_HD_NOINLINE static __host__ __device__ __noinline__
+#endif
 #else
 #define MG_HD static inline
 #define MG_HD_NOINLINE static
@@ -337,26 +343,23 @@ MG_HD void mg_collide(const ShapeView& a, const ShapeView& b, const double* bba,
     } else {
       m.margin = sqrt(distsq) - mindist;
     }
-  } else if (a.kind == 0 && b.kind == 2) {
+  } else {
+    /* every remaining pair runs GJK/EPA; ONE call site, so that lanes holding different kind pairs
+     * (circle-poly, segment-poly, poly-poly) stay converged through the bulk of the work */
     ClosestPts pts = mg_gjk(a, b, bba, bbb);
-    if (pts.d <= a.radius + b.radius) {
-      d2 n = m.n = pts.n;
-      manifold_push(m, dadd(pts.a, dmul(n, a.radius)), dadd(pts.b, dmul(n, -b.radius)), 0);
+    if (a.kind == 0) {
+      if (pts.d <= a.radius + b.radius) {
+        d2 n = m.n = pts.n;
+        manifold_push(m, dadd(pts.a, dmul(n, a.radius)), dadd(pts.b, dmul(n, -b.radius)), 0);
+      } else {
+        m.margin = pts.d - (a.radius + b.radius);
+      }
+    } else if (pts.d - a.radius - b.radius <= 0.0) {
+      SupEdge e1 = (a.kind == 1) ? support_edge_segment(a, pts.n) : support_edge_poly(a, pts.n);
+      contact_points(e1, support_edge_poly(b, dneg(pts.n)), pts, m);
     } else {
-      m.margin = pts.d - (a.radius + b.radius);
+      m.margin = pts.d - a.radius - b.radius;
     }
-  } else if (a.kind == 1 && b.kind == 2) {
-    ClosestPts pts = mg_gjk(a, b, bba, bbb);
-    if (pts.d - a.radius - b.radius <= 0.0)
-      contact_points(support_edge_segment(a, pts.n), support_edge_poly(b, dneg(pts.n)), pts, m);
-    else
-      m.margin = pts.d - a.radius - b.radius;
-  } else if (a.kind == 2 && b.kind == 2) {
-    ClosestPts pts = mg_gjk(a, b, bba, bbb);
-    if (pts.d - a.radius - b.radius <= 0.0)
-      contact_points(support_edge_poly(a, pts.n), support_edge_poly(b, dneg(pts.n)), pts, m);
-    else
-      m.margin = pts.d - a.radius - b.radius;
   }
 }
 

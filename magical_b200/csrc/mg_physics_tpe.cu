@@ -7,6 +7,7 @@
  * bounded by shared memory (about 1.7-2.2 KB per environment), which is what sizes `kcon` (the number of
  * solver contacts held on chip; rarer, larger contact sets continue in a per-environment spill area in HBM).
  */
+#define MG_NP_FORCE_INLINE
 #include "mg_physics_tpe.h"
 
 #define TPE_THREADS 32
@@ -25,12 +26,12 @@ k_physics_tpe(EnvState* __restrict__ states, const DeviceScene* __restrict__ sce
   Tpe<TPE_THREADS> T;
   T.wd = tpe_words + threadIdx.x;
   T.wf = reinterpret_cast<float*>(tpe_words) + threadIdx.x;
+  T.wh = reinterpret_cast<uint16_t*>(tpe_words) + threadIdx.x;
   T.L = L;
   T.spill = spill ? spill + (size_t)env * (size_t)((TPE_MAX_CONTACTS - L.kcon) * TPE_CON_WORDS) : nullptr;
   T.slotmap = 0;
   T.static_slot = 0;
-  float sep[MG_MAX_BPAIRS];
-  tpe_env_step<TPE_THREADS>(T, G, ds, actions[env], sep, live);
+  tpe_env_step<TPE_THREADS>(T, G, ds, actions[env], live);
 }
 
 size_t mg_tpe_smem_bytes(const TpeLayout* L) { return (size_t)L->words * sizeof(double) * TPE_THREADS; }

@@ -43,8 +43,10 @@
 
 #if defined(__CUDACC__)
 #define MG_HDM __host__ __device__ __forceinline__
+#define TPE_NOINLINE static __host__ __device__ __noinline__
 #else
 #define MG_HDM inline
+#define TPE_NOINLINE static
 #endif
 #if defined(__CUDA_ARCH__)
 #define TPE_LDG(p) __ldg(p)
@@ -93,11 +95,12 @@ struct TpeLayout {
   int nblocks;
   int off_bv, off_pr, off_bj, off_path, off_con;
   int kcon;     /* contacts that fit in the private words */
-  int off_it, nitems; /* narrowphase work items of the sub-step (one word each) */
+  int off_it, nitems; /* narrowphase work items of the sub-step (32 bits each) */
+  int off_sep;        /* separation cache: one 16-bit truncated float per candidate group pair */
   int words;    /* 8-byte words per environment */
 };
 
-static inline TpeLayout tpe_make_layout(int nslots, int nblocks, int ncgroups, int kcon, int nitems) {
+static inline TpeLayout tpe_make_layout(int nslots, int nblocks, int ncgroups, int nbpairs, int kcon, int nitems) {
   TpeLayout L;
   L.nslots = nslots;
   L.nblocks = nblocks;
@@ -111,16 +114,18 @@ static inline TpeLayout tpe_make_layout(int nslots, int nblocks, int ncgroups, i
   L.kcon = con_words / TPE_CON_WORDS;
   if (L.kcon > TPE_MAX_CONTACTS) L.kcon = TPE_MAX_CONTACTS;
   L.off_it = L.off_con + con_words;
-  L.nitems = nitems < 1 ? 1 : nitems;
-  L.words = L.off_it + L.nitems;
+  L.nitems = nitems < 2 ? 2 : (nitems > 64 ? 64 : (nitems + 1) / 2 * 2); /* item indices are 6 bits */
+  L.off_sep = L.off_it + L.nitems / 2;
+  L.words = L.off_sep + (nbpairs + 3) / 4;
   return L;
 }
 
 /* accessors over one environment's private words; S = distance (in words) between consecutive words */
 template <int S>
 struct Tpe {
-  double* wd;
+  double* wd;   /* the three views of the private words, each already offset by the lane */
   float* wf;
+  uint16_t* wh;
   TpeLayout L;
   double* spill; /* [TPE_MAX_CONTACTS - kcon][TPE_CON_WORDS] contiguous, or null */
   uint64_t slotmap;
@@ -131,7 +136,8 @@ struct Tpe {
   MG_HDM double& BJ(int b, int k) const { return wd[(L.off_bj + b * 4 + k) * S]; } /* pivot x,y  gear  gear bias */
   MG_HDM float& path(int s) const { return wf[(L.off_path * 2 + s) * S]; }
   MG_HDM float& gbb(int g, int k) const { return wf[(L.off_con * 2 + g * 4 + k) * S]; }
-  MG_HDM uint64_t& IT(int k) const { return reinterpret_cast<uint64_t*>(wd)[(L.off_it + k) * S]; }
+  MG_HDM uint32_t& IT(int k) const { return reinterpret_cast<uint32_t*>(wf)[(L.off_it * 2 + k) * S]; }
+  MG_HDM uint16_t& SEP(int p) const { return wh[(L.off_sep * 4 + p) * S]; }
   MG_HDM int slot(int body) const { /* body index or <0 / MG_MAX_BODIES for the static body */
     return (body < 0 || body >= MG_MAX_BODIES) ? static_slot : (int)((slotmap >> (4 * body)) & 15u);
   }
@@ -172,8 +178,8 @@ extern long tpe_stats[8]; /* host instrumentation: 0 sub-steps, 1 items, 2 items
 #else
 #define TPE_STAT(i) ((void)0)
 #endif
-#define TPE_IT_LAST (1ull << 24)
-#define TPE_IT_CONT (1ull << 25)
+#define TPE_IT_LAST (1u << 24)
+#define TPE_IT_CONT (1u << 25)
 #define TPE_NL(S) ((S) > 1 ? 32 : 1) /* lanes that cooperate: the warp on the device, one lane on the host */
 
 MG_HD bool tpe_f4_overlap(float4 a, float4 b) { return a.x <= b.z && b.x <= a.z && a.y <= b.w && b.y <= a.w; }
@@ -181,6 +187,48 @@ MG_HD bool tpe_f4_overlap(float4 a, float4 b) { return a.x <= b.z && b.x <= a.z 
 MG_HD double tpe_f4_gap(float4 a, float4 b) {
   return dmaxf(dmaxf((double)b.x - (double)a.z, (double)a.x - (double)b.z),
                dmaxf((double)b.y - (double)a.w, (double)a.y - (double)b.w));
+}
+
+/* Separation cache entry of candidate pair p: the value of path[a] + path[b] at which the measured
+ * separation expires, kept as the upper 16 bits of the float (truncation rounds a positive limit DOWN,
+ * i.e. towards re-measuring early); 0 = no valid measurement. */
+template <int S> struct Tpe;
+template <int S> MG_HD float tpe_sep_get(const Tpe<S>& T, int p) {
+  const uint32_t bits = (uint32_t)T.SEP(p) << 16;
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+template <int S> MG_HD void tpe_sep_set(const Tpe<S>& T, int p, float limit) {
+  uint32_t bits;
+  memcpy(&bits, &limit, 4);
+  T.SEP(p) = (limit > 0.0f) ? (uint16_t)(bits >> 16) : (uint16_t)0;
+}
+
+#ifndef TPE_MAX_SURV
+#define TPE_MAX_SURV 10 /* survivors per environment and sub-step that go through the cooperative GJK stage */
+#endif
+
+/* 6-bit "level" of a positive separation margin: the largest value 2^e * {1, 1.25, 1.5} (e >= -20) not
+ * above it, so that level -> value is a LOWER bound (exact in binary).  Level 1 = 2^-20, below the
+ * caching threshold; level 0 is reserved for "needs / produced a narrowphase result". */
+MG_HD int tpe_level(double m) {
+  if (!(m > 9.5367431640625e-07)) return 1; /* 2^-20 */
+  unsigned long long bits;
+  memcpy(&bits, &m, 8);
+  const int e = (int)((bits >> 52) & 0x7FFull) - 1023;
+  const int top2 = (int)((bits >> 50) & 3ull); /* mantissa >= .25 / .5 / .75 */
+  const int k = top2 >= 2 ? 2 : top2;
+  const int level = 3 * (e + 20) + k + 1;
+  return level > 63 ? 63 : level;
+}
+MG_HD double tpe_level_value(int level) {
+  const int L = level - 1;
+  const int e = L / 3 - 20, k = L % 3;
+  const unsigned long long bits = ((unsigned long long)(e + 1023) << 52) | ((unsigned long long)k << 50);
+  double v;
+  memcpy(&v, &bits, 8);
+  return v;
 }
 
 /* warp cooperation primitives; on the host (S == 1) the warp is a single lane */
@@ -231,6 +279,23 @@ template <int S> MG_HD int tpe_max(int v) {
 #endif
   return v;
 }
+template <int S> MG_HD void tpe_sync() {
+#if defined(__CUDA_ARCH__)
+  if (S > 1) __syncwarp();
+#endif
+}
+/* owner of queue entry j, given every lane's exclusive prefix of its entry count: the last lane whose
+ * prefix is <= j (all lanes must call this together) */
+template <int S> MG_HD int tpe_find_owner(int excl, int j) {
+  int lo = 0, hi = TPE_NL(S) - 1;
+#pragma unroll
+  for (int step = 0; step < 5; step++) {
+    const int mid = (lo + hi + 1) >> 1;
+    const int e = tpe_shfl<S>(excl, mid);
+    if (lo < hi) { if (e <= j) lo = mid; else hi = mid - 1; }
+  }
+  return lo;
+}
 
 template <int S>
 MG_HD ShapeView tpe_view(const Tpe<S>& T, const DeviceScene* ds, int si) {
@@ -265,10 +330,21 @@ MG_HD float4 tpe_shape_box(const Tpe<S>& T, const DeviceScene* ds, int si) {
                      ds->aux.static_bb[si][3]);
 }
 
+/* gap between the exact boxes of two shapes: > 0 = disjoint (a lower bound of the shapes' distance) */
+template <int S>
+MG_HD double tpe_pair_gap(const Tpe<S>& T, const DeviceScene* ds, int ia, int ib) {
+  ShapeView va = tpe_view(T, ds, ia), vb = tpe_view(T, ds, ib);
+  double bba[4], bbb[4];
+  sv_bb(va, bba);
+  sv_bb(vb, bbb);
+  if (bb_intersects(bba, bbb)) return -1.0;
+  return dmaxf(dmaxf(bbb[0] - bba[2], bba[0] - bbb[2]), dmaxf(bbb[1] - bba[3], bba[1] - bbb[3]));
+}
+
 /* Exact narrowphase of one shape pair (kinds already ordered).  When the exact boxes are disjoint the
  * gap between them is a valid lower bound of the shapes' distance and is reported as the margin. */
 template <int S>
-MG_HD_NOINLINE void tpe_narrow_pair(const Tpe<S>* Tp, const DeviceScene* ds, int ia, int ib, Manifold* out) {
+TPE_NOINLINE void tpe_narrow_pair(const Tpe<S>* Tp, const DeviceScene* ds, int ia, int ib, Manifold* out) {
   const Tpe<S>& T = *Tp;
   ShapeView va = tpe_view(T, ds, ia), vb = tpe_view(T, ds, ib);
   double bba[4], bbb[4];
@@ -377,9 +453,9 @@ MG_HD void tpe_pin(const TpeJC& c, const TpePin& pn, double& acc, double& vax, d
   wb += c.ib * (r2.x * jy - r2.y * jx);
 }
 
-/* One env-step of one environment.  `sep` is per-thread scratch of MG_MAX_BPAIRS floats. */
+/* One env-step of one environment. */
 template <int S>
-MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* __restrict__ ds, int action, float* sep,
+MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* __restrict__ ds, int action,
                          const bool live) {
   const mg_scene_t& sc = ds->s;
   const mg_scene_aux_t& ax = ds->aux;
@@ -421,7 +497,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     T.BJ(k, 2) = G->jacc[ax.tpe_bj_gear[k]].x;
     T.BJ(k, 3) = 0.0;
   }
-  for (int p = 0; p < nbp; p++) sep[p] = -1.0f;
+  for (int p = 0; p < nbp; p++) T.SEP(p) = 0;
   /* control body (kinematic) and the two eye bodies (no shapes) */
   double4 Pc = G->P[control], Vc = G->V[control], Bc = G->Bv[control];
   double4 Pe0 = G->P[eye0], Ve0 = G->V[eye0], Be0 = G->Bv[eye0];
@@ -499,64 +575,57 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     TPE_INTEGRATE_REG(Pe0, Ve0, Be0, Re0);
     TPE_INTEGRATE_REG(Pe1, Ve1, Be1, Re1);
 
-    /* ---- conservative fp32 boxes of the collision groups */
+    /* ---- conservative fp32 boxes of the collision groups: body position +- reach (the largest distance of
+     * any point of the body's shapes from its origin), which needs no vertex transforms; the exact boxes
+     * are only computed for the few pairs that get past this filter and the separation cache */
     for (int g = 0; g < ncg; g++) {
-      const int s0 = sc.cgroups[g].shape0, n = sc.cgroups[g].nshape;
-      float l = INFINITY, b = INFINITY, r = -INFINITY, t = -INFINITY;
-      for (int k = 0; k < n; k++) {
-        const float4 bx = tpe_shape_box(T, ds, s0 + k);
-        l = fminf(l, bx.x); b = fminf(b, bx.y); r = fmaxf(r, bx.z); t = fmaxf(t, bx.w);
+      const int gbody = sc.cgroups[g].body;
+      float l, b, r, t;
+      if (gbody >= 0) {
+        const int s = T.slot(gbody);
+        const double reach = TPE_LDG(&ax.body_reach[gbody]);
+        const double x = T.PR(s, 0), y = T.PR(s, 1);
+        l = tpe_d2f_rd(x - reach); b = tpe_d2f_rd(y - reach); r = tpe_d2f_ru(x + reach); t = tpe_d2f_ru(y + reach);
+      } else {
+        const int s0 = sc.cgroups[g].shape0, n = sc.cgroups[g].nshape;
+        l = INFINITY; b = INFINITY; r = -INFINITY; t = -INFINITY;
+        for (int k = 0; k < n; k++) {
+          const float4 bx = tpe_shape_box(T, ds, s0 + k);
+          l = fminf(l, bx.x); b = fminf(b, bx.y); r = fmaxf(r, bx.z); t = fmaxf(t, bx.w);
+        }
       }
       T.gbb(g, 0) = l; T.gbb(g, 1) = b; T.gbb(g, 2) = r; T.gbb(g, 3) = t;
     }
 
-    /* ---- broadphase (own environment): canonical pair list -> the shape pairs that need the exact
-     * narrowphase, as "items" in the private words.  Filters, all exact: group boxes, the cached
-     * separation of the group pair, per-shape boxes for multi-shape groups.  A filtered pair contributes
-     * the gap between its (conservative) boxes to the group pair's separation margin. */
+    /* ---- broadphase (own environment): canonical pair list -> work items for the exact narrowphase.
+     * Only trivial per-lane work happens here (lanes diverge): group boxes, the cached separation of the
+     * group pair, then one 32-bit item per shape pair.  The exact per-shape boxes are tested by the lanes
+     * that execute the items, converged, inside tpe_narrow_pair. */
     int n_items = 0;
     bool truncated = false;
     int res_p = 0, res_i = 0, res_k = 0;
-    double res_gm = MG_INF;
     for (int p = 0; p < nbp && !truncated; p++) {
       const int ga = sc.bpairs[p][0], gb = sc.bpairs[p][1];
-      const float4 A = make_float4(T.gbb(ga, 0), T.gbb(ga, 1), T.gbb(ga, 2), T.gbb(ga, 3));
-      const float4 B = make_float4(T.gbb(gb, 0), T.gbb(gb, 1), T.gbb(gb, 2), T.gbb(gb, 3));
-      if (!tpe_f4_overlap(A, B)) continue;
+      if (!(T.gbb(ga, 0) <= T.gbb(gb, 2) && T.gbb(gb, 0) <= T.gbb(ga, 2) && T.gbb(ga, 1) <= T.gbb(gb, 3) &&
+            T.gbb(gb, 1) <= T.gbb(ga, 3)))
+        continue;
       TPE_STAT(3);
       const int sla = T.slot(sc.cgroups[ga].body), slb = T.slot(sc.cgroups[gb].body);
       const float travelled = tpe_fadd_ru(T.path(sla), T.path(slb));
-      if (travelled < sep[p]) { TPE_STAT(4); continue; }
+      if (travelled < tpe_sep_get(T, p)) { TPE_STAT(4); continue; }
       const int sa0 = sc.cgroups[ga].shape0, na = sc.cgroups[ga].nshape;
       const int sb0 = sc.cgroups[gb].shape0, nbs = sc.cgroups[gb].nshape;
-      double gm = MG_INF;
       const int first_item = n_items;
-      for (int i = 0; i < na && !truncated; i++) {
-        const float4 Ai = (na == 1) ? A : tpe_shape_box(T, ds, sa0 + i);
-        if (na > 1 && !tpe_f4_overlap(Ai, B)) { gm = dminf(gm, tpe_f4_gap(Ai, B)); continue; }
+      for (int i = 0; i < na && !truncated; i++)
         for (int k = 0; k < nbs; k++) {
-          if (na > 1 || nbs > 1) {
-            const float4 Bk = (nbs == 1) ? B : tpe_shape_box(T, ds, sb0 + k);
-            if (!tpe_f4_overlap(Ai, Bk)) { gm = dminf(gm, tpe_f4_gap(Ai, Bk)); continue; }
-          }
-          if (n_items == T.L.nitems) { truncated = true; res_p = p; res_i = i; res_k = k; res_gm = gm; break; }
+          if (n_items == T.L.nitems) { truncated = true; res_p = p; res_i = i; res_k = k; break; }
           int ia = sa0 + i, ib = sb0 + k;
           if (sc.shapes[ia].kind > sc.shapes[ib].kind) { int t = ia; ia = ib; ib = t; }
-          T.IT(n_items++) = (uint64_t)(uint32_t)(ia | (ib << 8) | (p << 16));
+          T.IT(n_items++) = (uint32_t)(ia | (ib << 8) | (p << 16));
           TPE_STAT(1);
         }
-      }
-      if (n_items > first_item) {
-        /* the pair's last item carries the box-filter part of its margin; LAST = settle sep[p] after it,
-         * CONT = the pair continues in the serial tail below */
-        float gmf = gm < 3.0e38 ? tpe_d2f_rd(gm) : 3.0e38f;
-        uint32_t gbits;
-        memcpy(&gbits, &gmf, 4);
-        T.IT(n_items - 1) = (T.IT(n_items - 1) & 0xFFFFFFFFull) | (truncated ? TPE_IT_CONT : TPE_IT_LAST) |
-                            ((uint64_t)gbits << 32);
-      } else if (!truncated) {
-        sep[p] = (gm > 1e-6 && gm < MG_INF) ? tpe_fadd_rd(travelled, tpe_d2f_rd(gm * 0.999999 - 1e-9)) : -1.0f;
-      }
+      /* LAST = settle the pair's separation after this item; CONT = the pair continues in the serial tail */
+      if (n_items > first_item) T.IT(n_items - 1) |= truncated ? TPE_IT_CONT : TPE_IT_LAST;
     }
 
     /* ---- narrowphase + contact cache lookup (cpCollide + cpArbiterUpdate).
@@ -567,11 +636,9 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     bool too_many = false;
     uint32_t cache_used = 0u;
     const int kcap = T.spill ? TPE_MAX_CONTACTS : T.L.kcon;
-    double gm_run = MG_INF;
     /* turn one pair's manifold into solver contacts of this environment */
     auto take_manifold = [&](int ia, int ib, const Manifold& m) {
-      if (m.count == 0) { gm_run = dminf(gm_run, m.margin > 0.0 ? m.margin : 0.0); return; }
-      gm_run = 0.0;
+      if (m.count == 0) return;
       TPE_STAT(2);
       if (ncon + m.count > kcap) { too_many = true; ncon += m.count; return; }
       int ba = sc.shapes[ia].body, bb = sc.shapes[ib].body;
@@ -608,88 +675,128 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     auto settle_sep = [&](int p, double gm) {
       const int sla = T.slot(sc.cgroups[sc.bpairs[p][0]].body), slb = T.slot(sc.cgroups[sc.bpairs[p][1]].body);
       const float travelled = tpe_fadd_ru(T.path(sla), T.path(slb));
-      sep[p] = (gm > 1e-6 && gm < MG_INF) ? tpe_fadd_rd(travelled, tpe_d2f_rd(gm * 0.999999 - 1e-9)) : -1.0f;
+      tpe_sep_set(T, p, (gm > 1e-6 && gm < MG_INF) ? tpe_fadd_rd(travelled, tpe_d2f_rd(gm * 0.999999 - 1e-9)) : -1.0f);
     };
     {
       const int lane = tpe_lane<S>();
-      const int incl = tpe_scan_incl<S>(n_items);
-      const int excl = incl - n_items;
-      const int n_all = tpe_shfl<S>(incl, TPE_NL(S) - 1);
-      int consumed = 0;
-      for (int base = 0; base < n_all; base += TPE_NL(S)) {
-        const int j = base + lane;
-        /* owner of queue entry j: the last lane whose exclusive prefix is <= j */
-        int lo = 0, hi = TPE_NL(S) - 1;
-#pragma unroll
-        for (int step = 0; step < 5; step++) {
-          const int mid = (lo + hi + 1) >> 1;
-          const int e = tpe_shfl<S>(excl, mid);
-          if (lo < hi) { if (e <= j) lo = mid; else hi = mid - 1; }
+      /* ---- stage A: exact boxes of every item, one item per lane.  A pair whose boxes are disjoint is
+       * settled here: the gap is a lower bound of the shapes' distance and goes into the item's level. */
+      {
+        const int incl = tpe_scan_incl<S>(n_items);
+        const int excl = incl - n_items;
+        const int n_all = tpe_shfl<S>(incl, TPE_NL(S) - 1);
+        for (int base = 0; base < n_all; base += TPE_NL(S)) {
+          const int j = base + lane;
+          const int owner = tpe_find_owner<S>(excl, j);
+          const int oexcl = tpe_shfl<S>(excl, owner);
+          Tpe<S> To = T;
+          To.wd = T.wd - lane + owner; To.wf = T.wf - lane + owner; To.wh = T.wh - lane + owner;
+          To.slotmap = tpe_shfl64<S>(T.slotmap, owner);
+          To.static_slot = tpe_shfl<S>(T.static_slot, owner);
+          const DeviceScene* dso = (const DeviceScene*)tpe_shfl64<S>((uint64_t)ds, owner);
+          if (j < n_all) {
+            const uint32_t it = To.IT(j - oexcl);
+            const double gap = tpe_pair_gap(To, dso, (int)(it & 0xFFu), (int)((it >> 8) & 0xFFu));
+            if (gap > 0.0) To.IT(j - oexcl) = it | ((uint32_t)tpe_level(gap) << 26);
+          }
         }
-        const int owner = lo;
-        const int oexcl = tpe_shfl<S>(excl, owner);
-        Tpe<S> To = T;
-        To.wd = T.wd - lane + owner;
-        To.wf = T.wf - lane + owner;
-        To.slotmap = tpe_shfl64<S>(T.slotmap, owner);
-        To.static_slot = tpe_shfl<S>(T.static_slot, owner);
-        const DeviceScene* dso = (const DeviceScene*)tpe_shfl64<S>((uint64_t)ds, owner);
-        Manifold m;
-        m.count = 0; m.margin = -1.0; m.n = D2(0, 0);
-        m.p1[0] = m.p1[1] = m.p2[0] = m.p2[1] = D2(0, 0);
-        m.hash[0] = m.hash[1] = 0u;
-        if (j < n_all) {
-          const uint32_t it = (uint32_t)To.IT(j - oexcl);
-          tpe_narrow_pair<S>(&To, dso, (int)(it & 0xFFu), (int)((it >> 8) & 0xFFu), &m);
+        tpe_sync<S>();
+      }
+      /* ---- the items that need GJK ("survivors"), as a packed list of item indices (6 bits each) */
+      uint64_t surv = 0;
+      int n_surv = 0;
+      for (int k = 0; k < n_items; k++)
+        if ((T.IT(k) >> 26) == 0u) {
+          if (n_surv < TPE_MAX_SURV) surv |= (uint64_t)k << (6 * n_surv);
+          n_surv++;
         }
-        /* owners pull the results of their entries in this round, in order */
-        const int a = (excl > base ? excl : base) - base;
-        const int b = (incl < base + TPE_NL(S) ? incl : base + TPE_NL(S)) - base;
-        const int cnt = b > a ? b - a : 0;
-        const int most = tpe_max<S>(cnt);
-        for (int t = 0; t < most; t++) {
-          const int src = t < cnt ? a + t : lane;
-          Manifold r;
-          r.count = tpe_shfl<S>(m.count, src);
-          r.margin = tpe_shfld<S>(m.margin, src);
-          r.n.x = tpe_shfld<S>(m.n.x, src); r.n.y = tpe_shfld<S>(m.n.y, src);
-          r.p1[0].x = tpe_shfld<S>(m.p1[0].x, src); r.p1[0].y = tpe_shfld<S>(m.p1[0].y, src);
-          r.p2[0].x = tpe_shfld<S>(m.p2[0].x, src); r.p2[0].y = tpe_shfld<S>(m.p2[0].y, src);
-          r.p1[1].x = tpe_shfld<S>(m.p1[1].x, src); r.p1[1].y = tpe_shfld<S>(m.p1[1].y, src);
-          r.p2[1].x = tpe_shfld<S>(m.p2[1].x, src); r.p2[1].y = tpe_shfld<S>(m.p2[1].y, src);
-          r.hash[0] = (unsigned)tpe_shfl<S>((int)m.hash[0], src);
-          r.hash[1] = (unsigned)tpe_shfl<S>((int)m.hash[1], src);
-          if (t < cnt) {
-            const uint64_t itw = T.IT(consumed++);
-            const uint32_t it = (uint32_t)itw;
-            take_manifold((int)(it & 0xFFu), (int)((it >> 8) & 0xFFu), r);
-            if (itw & (TPE_IT_LAST | TPE_IT_CONT)) {
-              float gmf;
-              const uint32_t gbits = (uint32_t)(itw >> 32);
-              memcpy(&gmf, &gbits, 4);
-              const double gm = dminf(gm_run, gmf < 3.0e38f ? (double)gmf : MG_INF);
-              if (itw & TPE_IT_LAST) { settle_sep((int)((it >> 16) & 0xFFu), gm); gm_run = MG_INF; }
-              else gm_run = gm; /* carried into the serial tail */
+      const int n_coop = n_surv < TPE_MAX_SURV ? n_surv : TPE_MAX_SURV;
+      /* ---- stage B: GJK / EPA / clipping of the survivors, one per lane; the owners then pull their
+       * results, in canonical order, with shuffles */
+      {
+        const int incl = tpe_scan_incl<S>(n_coop);
+        const int excl = incl - n_coop;
+        const int n_all = tpe_shfl<S>(incl, TPE_NL(S) - 1);
+        int consumed = 0;
+        for (int base = 0; base < n_all; base += TPE_NL(S)) {
+          const int j = base + lane;
+          const int owner = tpe_find_owner<S>(excl, j);
+          const int oexcl = tpe_shfl<S>(excl, owner);
+          const uint64_t osurv = tpe_shfl64<S>(surv, owner);
+          Tpe<S> To = T;
+          To.wd = T.wd - lane + owner; To.wf = T.wf - lane + owner; To.wh = T.wh - lane + owner;
+          To.slotmap = tpe_shfl64<S>(T.slotmap, owner);
+          To.static_slot = tpe_shfl<S>(T.static_slot, owner);
+          const DeviceScene* dso = (const DeviceScene*)tpe_shfl64<S>((uint64_t)ds, owner);
+          Manifold m;
+          m.count = 0; m.margin = -1.0; m.n = D2(0, 0);
+          m.p1[0] = m.p1[1] = m.p2[0] = m.p2[1] = D2(0, 0);
+          m.hash[0] = m.hash[1] = 0u;
+          if (j < n_all) {
+            const uint32_t it = To.IT((int)((osurv >> (6 * (j - oexcl))) & 63u));
+            tpe_narrow_pair<S>(&To, dso, (int)(it & 0xFFu), (int)((it >> 8) & 0xFFu), &m);
+          }
+          const int a = (excl > base ? excl : base) - base;
+          const int b = (incl < base + TPE_NL(S) ? incl : base + TPE_NL(S)) - base;
+          const int cnt = b > a ? b - a : 0;
+          const int most = tpe_max<S>(cnt);
+          for (int t = 0; t < most; t++) {
+            const int src = t < cnt ? a + t : lane;
+            Manifold r;
+            r.count = tpe_shfl<S>(m.count, src);
+            r.margin = tpe_shfld<S>(m.margin, src);
+            r.n.x = tpe_shfld<S>(m.n.x, src); r.n.y = tpe_shfld<S>(m.n.y, src);
+            r.p1[0].x = tpe_shfld<S>(m.p1[0].x, src); r.p1[0].y = tpe_shfld<S>(m.p1[0].y, src);
+            r.p2[0].x = tpe_shfld<S>(m.p2[0].x, src); r.p2[0].y = tpe_shfld<S>(m.p2[0].y, src);
+            r.p1[1].x = tpe_shfld<S>(m.p1[1].x, src); r.p1[1].y = tpe_shfld<S>(m.p1[1].y, src);
+            r.p2[1].x = tpe_shfld<S>(m.p2[1].x, src); r.p2[1].y = tpe_shfld<S>(m.p2[1].y, src);
+            r.hash[0] = (unsigned)tpe_shfl<S>((int)m.hash[0], src);
+            r.hash[1] = (unsigned)tpe_shfl<S>((int)m.hash[1], src);
+            if (t < cnt) {
+              const int k = (int)((surv >> (6 * consumed)) & 63u);
+              consumed++;
+              const uint32_t it = T.IT(k);
+              take_manifold((int)(it & 0xFFu), (int)((it >> 8) & 0xFFu), r);
+              if (r.count == 0 && r.margin > 0.0) T.IT(k) = it | ((uint32_t)tpe_level(r.margin) << 26);
             }
           }
         }
       }
+      /* survivors beyond the packed list (rare): by the owner itself, still in canonical order */
+      if (n_surv > TPE_MAX_SURV) {
+        const int last_coop = (int)((surv >> (6 * (TPE_MAX_SURV - 1))) & 63u);
+        for (int k = last_coop + 1; k < n_items; k++) {
+          const uint32_t it = T.IT(k);
+          if ((it >> 26) != 0u) continue;
+          Manifold m;
+          tpe_narrow_pair<S>(&T, ds, (int)(it & 0xFFu), (int)((it >> 8) & 0xFFu), &m);
+          take_manifold((int)(it & 0xFFu), (int)((it >> 8) & 0xFFu), m);
+          if (m.count == 0 && m.margin > 0.0) T.IT(k) = it | ((uint32_t)tpe_level(m.margin) << 26);
+        }
+      }
+    }
+    /* ---- separation cache: per candidate pair, the smallest margin over its items (level 0 = touching
+     * or unknown -> not cached) */
+    double gm_run = MG_INF;
+    for (int k = 0; k < n_items; k++) {
+      const uint32_t it = T.IT(k);
+      const uint32_t lvl = it >> 26;
+      gm_run = dminf(gm_run, lvl ? tpe_level_value((int)lvl) : 0.0);
+      if (it & TPE_IT_LAST) { settle_sep((int)((it >> 16) & 0xFFu), gm_run); gm_run = MG_INF; }
+      /* CONT: gm_run is carried into the serial tail */
     }
     if (truncated) {
-      /* serial tail (rare: more candidate pairs than item words): the remaining pairs in canonical order,
-       * without the box filters (the boxes' words now hold contacts) -- tpe_narrow_pair tests the exact
-       * boxes itself */
-      double gm = dminf(gm_run, res_gm);
+      /* serial tail (rare: more candidate pairs than item words): the remaining pairs in canonical order;
+       * tpe_narrow_pair tests the exact boxes itself */
       for (int p = res_p; p < nbp; p++) {
         const int ga = sc.bpairs[p][0], gb = sc.bpairs[p][1];
         const int sa0 = sc.cgroups[ga].shape0, na = sc.cgroups[ga].nshape;
         const int sb0 = sc.cgroups[gb].shape0, nbs = sc.cgroups[gb].nshape;
         if (p != res_p) {
           const int sla = T.slot(sc.cgroups[ga].body), slb = T.slot(sc.cgroups[gb].body);
-          if (tpe_fadd_ru(T.path(sla), T.path(slb)) < sep[p]) continue;
-          gm = MG_INF;
+          if (tpe_fadd_ru(T.path(sla), T.path(slb)) < tpe_sep_get(T, p)) continue;
+          gm_run = MG_INF;
         }
-        gm_run = MG_INF;
         for (int i = (p == res_p ? res_i : 0); i < na; i++)
           for (int k = (p == res_p && i == res_i ? res_k : 0); k < nbs; k++) {
             int ia = sa0 + i, ib = sb0 + k;
@@ -697,8 +804,9 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
             Manifold m;
             tpe_narrow_pair<S>(&T, ds, ia, ib, &m);
             take_manifold(ia, ib, m);
+            gm_run = dminf(gm_run, (m.count == 0 && m.margin > 0.0) ? m.margin : 0.0);
           }
-        settle_sep(p, dminf(gm, gm_run));
+        settle_sep(p, gm_run);
       }
     }
     if (too_many) {

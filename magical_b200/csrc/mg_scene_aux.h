@@ -300,6 +300,7 @@ static inline const char* mg_build_scene_aux(const mg_scene_t* s, mg_scene_aux_t
     for (int k = 0; k < sh->nvert; k++) {
       double d = sqrt(s->cverts[sh->vert0 + k][0] * s->cverts[sh->vert0 + k][0] +
                       s->cverts[sh->vert0 + k][1] * s->cverts[sh->vert0 + k][1]) + sh->radius;
+      d = d * (1.0 + 1e-9) + 1e-12; /* strictly above the rounded rotated vertices: the reach is used as a bound */
       if (d > aux->body_reach[sh->body]) aux->body_reach[sh->body] = d;
     }
   }

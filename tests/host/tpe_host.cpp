@@ -14,7 +14,6 @@ struct TpeHostEnv {
   TpeLayout L;
   std::vector<double> words;
   std::vector<double> spill;
-  float sep[MG_MAX_BPAIRS];
   int use_spill;
 };
 
@@ -42,7 +41,7 @@ TpeHostEnv* tpeh_create(const mg_scene_t* scene, int kcon, int use_spill, int ni
   TpeHostEnv* e = new TpeHostEnv();
   e->ds.s = *scene;
   if (mg_build_scene_aux(scene, &e->ds.aux) || !e->ds.aux.tpe_ok) { delete e; return nullptr; }
-  e->L = tpe_make_layout(e->ds.aux.tpe_nslots, e->ds.aux.tpe_nblocks, scene->n_cgroups, kcon, nitems);
+  e->L = tpe_make_layout(e->ds.aux.tpe_nslots, e->ds.aux.tpe_nblocks, scene->n_cgroups, scene->n_bpairs, kcon, nitems);
   e->words.assign((size_t)e->L.words, 0.0);
   e->spill.assign((size_t)TPE_MAX_CONTACTS * TPE_CON_WORDS, 0.0);
   e->use_spill = use_spill;
@@ -58,11 +57,12 @@ void tpeh_step(TpeHostEnv* e, int action) {
   Tpe<1> T;
   T.wd = e->words.data();
   T.wf = reinterpret_cast<float*>(e->words.data());
+  T.wh = reinterpret_cast<uint16_t*>(e->words.data());
   T.L = e->L;
   T.spill = e->use_spill ? e->spill.data() : nullptr;
   T.slotmap = 0;
   T.static_slot = 0;
-  tpe_env_step<1>(T, &e->st, &e->ds, action, e->sep, true);
+  tpe_env_step<1>(T, &e->st, &e->ds, action, true);
   e->st.episode_steps++;
 }
 

@@ -33,8 +33,9 @@ def _compare(st, ost, tag):
     return nc
 
 
-def _rollout(rec, actions, kcon=8, spill=True, nitems=12):
-    env = TpeHostEnv(rec, kcon=kcon, spill=spill, nitems=nitems)
+def _rollout(rec, actions, kcon=8, spill=True, nitems=32, max_surv=None):
+    env = TpeHostEnv(rec, kcon=kcon, spill=spill, nitems=nitems,
+                     max_surv=max_surv)
     orc = OracleEnv(rec, det_sincos=True)
     most = 0
     for t, a in enumerate(actions):
@@ -94,6 +95,17 @@ def test_item_word_overflow_takes_the_serial_tail(nitems):
                 for _ in range(200)]
         most = _rollout(rec, acts, nitems=nitems)
         assert most >= 2
+
+
+def test_survivor_list_overflow_continues_serially():
+    """More GJK survivors than the packed cooperative list holds: the owner
+    finishes them itself, in canonical order."""
+    rec = make_demo_task('ClusterColour').build_scene()
+    rng = np.random.RandomState(4)
+    acts = [int(rng.randint(18)) if rng.rand() < 0.5
+            else int(rng.choice([1, 4, 7, 10, 13, 16])) for _ in range(240)]
+    most = _rollout(rec, acts, max_surv=1)
+    assert most >= 3
 
 
 def test_capacity_overflow_is_flagged_without_spill():

@@ -13,11 +13,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'host', 'tpe_host.cpp')
 LIB = os.path.join(HERE, 'host', 'libtpe_host.so')
 CUDA_INC = os.environ.get('CUDA_INC', '/usr/local/cuda/include')
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
+def lib(max_surv=None):
+    """max_surv: build a variant with a smaller cooperative-survivor list (to
+    exercise the owner-serial continuation)."""
+    global _libs
+    LIB = os.path.join(HERE, 'host', 'libtpe_host%s.so' % (
+        '' if max_surv is None else '_surv%d' % max_surv))
+    _lib = _libs.get(max_surv)
     if _lib is None:
         root = os.path.dirname(HERE)
         csrc = os.path.join(root, 'magical_b200', 'csrc')
@@ -27,8 +32,10 @@ def lib():
         if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(
                 map(os.path.getmtime, deps)):
             subprocess.run(['g++', '-O2', '-fPIC', '-shared', '-std=c++17',
-                            '-ffp-contract=off', '-I', CUDA_INC, '-o', LIB,
-                            SRC, '-lm'], check=True)
+                            '-ffp-contract=off', '-I', CUDA_INC]
+                           + ([] if max_surv is None
+                              else ['-DTPE_MAX_SURV=%d' % max_surv])
+                           + ['-o', LIB, SRC, '-lm'], check=True)
         L = ctypes.CDLL(LIB)
         vp, i32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
         L.tpeh_create.restype = vp
@@ -40,13 +47,14 @@ def lib():
         L.tpeh_set_pose.argtypes = [vp, i32, f64, f64, f64]
         L.tpeh_kcon.argtypes = [vp]
         L.tpeh_words.argtypes = [vp]
-        _lib = L
+        _libs[max_surv] = _lib = L
     return _lib
 
 
 class TpeHostEnv:
-    def __init__(self, scene_record, kcon=8, spill=True, nitems=12):
-        self._lib = lib()
+    def __init__(self, scene_record, kcon=8, spill=True, nitems=32,
+                 max_surv=None):
+        self._lib = lib(max_surv)
         self._scene = np.ascontiguousarray(scene_record).copy()
         self._h = self._lib.tpeh_create(self._scene.ctypes.data, kcon,
                                         int(spill), nitems)
