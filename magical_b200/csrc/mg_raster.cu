@@ -338,9 +338,10 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     }
   }
   __syncthreads();
-  /* D: span-table offsets (serial prefix; <= 192 entries) + oriented edge equations */
+  /* D: span-table offsets (warp 0) + oriented edge equations and, per polygon edge, the sample rows it
+   * can bound: row j is bounded by an edge only if j + 0.5 lies within one sample of the edge's own
+   * y-extent (the polygon is convex, so edges further away hold with a margin far above fp32 rounding) */
   if (tid < 32) {
-    /* warp 0: span-table offsets = exclusive prefix sum of the row counts */
     int off = 0;
     for (int base = 0; base < nrp; base += 32) {
       int p = base + tid;
@@ -364,28 +365,125 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     int lo = 0, hi = np - 1;
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= v) lo = mid; else hi = mid - 1; }
     const mg_prim_t& pr = sc.prims[lo];
-    if (pr.kind == MG_PRIM_LINELOOP) continue;
     int rp0 = s_off[MG_MAX_PRIMS + 1 + lo];
-    if (rp0 >= RMAXP) continue;
+    if (pr.kind == MG_PRIM_LINELOOP || rp0 >= RMAXP) {
+      vs.eaux[v] = make_float4(0.0f, 0.0f, __int_as_float(0), __int_as_float(0));
+      continue;
+    }
     int v0 = s_off[lo], n = pr.nvert, k = v - v0;
     float2 a = vs.verts[v0 + k], b = vs.verts[v0 + (k + 1) % n];
-    float sgn = vs.prims[rp0].sgn;
+    const RPrim& R = vs.prims[rp0];
+    float sgn = R.sgn;
     float A = a.y - b.y, B = b.x - a.x;
     float C = -fmaf(A, a.x, B * a.y);
     A *= sgn; B *= sgn; C *= sgn;
-    vs.edges[v] = make_float4(A, B, C, 0.0f);
+    vs.edges[v] = make_float4(A, B, C, __int_as_float(rp0));
     /* boundary column of this edge on row y: x*(y) = -(B y + C)/A = m y + q (an ESTIMATE only) */
     float inv = (A != 0.0f) ? __fdividef(1.0f, A) : 0.0f;
-    vs.eaux[v] = make_float4(-B * inv, -C * inv, fminf(a.y, b.y), fmaxf(a.y, b.y));
+    /* rows with  ymin_e - 1 <= j + 0.5 <= ymax_e + 1  (decided with the exact fp32 comparisons), clipped
+     * to the rows of the primitive that are not empty anyway */
+    const float elo = fminf(a.y, b.y) - 1.0f, ehi = fmaxf(a.y, b.y) + 1.0f;
+    int j0 = (int)ceilf(elo - 0.5f), j1 = (int)floorf(ehi - 0.5f);
+    while ((float)(j0 - 1) + 0.5f >= elo) j0--;
+    while ((float)j0 + 0.5f < elo) j0++;
+    while ((float)(j1 + 1) + 0.5f <= ehi) j1++;
+    while ((float)j1 + 0.5f > ehi) j1--;
+    int r0 = R.row0, r1 = R.row0 + R.nrows - 1;
+    while (r0 <= r1 && (float)r0 + 0.5f < R.ymin - 0.01f) r0++;
+    while (r1 >= r0 && (float)r1 + 0.5f > R.ymax + 0.01f) r1--;
+    j0 = max(j0, r0); j1 = min(j1, r1);
+    const int cnt = j1 >= j0 ? j1 - j0 + 1 : 0;
+    vs.eaux[v] = make_float4(-B * inv, -C * inv, __int_as_float(j0), __int_as_float(cnt));
   }
   __syncthreads();
-  /* E: spans, one work item per (primitive, row) */
-  const int nspan = s_misc[2];
-  for (int w = tid; w < nspan; w += nt) {
-    int lo = 0, hi = nrp - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (vs.prims[mid].span0 <= w) lo = mid; else hi = mid - 1; }
-    const RPrim& R = vs.prims[lo];
-    vs.spans[w] = row_span(R, vs.edges, vs.eaux, R.row0 + (w - R.span0));
+  /* E0: warp 0 turns the per-edge row counts into offsets (exclusive prefix) while the other warps
+   * initialise the span table: polygons start from their bounding columns (rows outside the vertices'
+   * y-extent are empty), thick line segments are solved directly per row */
+  const int nwarp = nt >> 5, wid = tid >> 5, lane = tid & 31;
+  if (wid == 0) {
+    int off = 0;
+    for (int base = 0; base < nv; base += 32) {
+      int v = base + lane;
+      int c = (v < nv) ? __float_as_int(vs.eaux[v].w) : 0;
+      int incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (v < nv) vs.eaux[v].w = __int_as_float(off + incl - c);
+      off += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_misc[3] = off;
+  } else {
+    for (int p = wid - 1; p < nrp; p += nwarp - 1) {
+      const RPrim R = vs.prims[p];
+      for (int r = lane; r < R.nrows; r += 32) {
+        const int j = R.row0 + r;
+        short2 sp;
+        if (R.ne > 0) {
+          const float y = (float)j + 0.5f;
+          const bool outside = (y > R.ymax + 0.01f || y < R.ymin - 0.01f);
+          sp = make_short2((short)R.col0, outside ? (short)(R.col0 - 1) : (short)R.col1);
+        } else {
+          sp = row_span(R, vs.edges, vs.eaux, j);
+        }
+        vs.spans[R.span0 + r] = sp;
+      }
+    }
+  }
+  __syncthreads();
+  /* E1: one work item per (polygon edge, row it can bound): the exact first / last covered column w.r.t.
+   * that edge, folded into the row's span with a compare-and-swap.  Every edge function is monotone in x,
+   * so the covered set of a row is [max of the lower bounds, min of the upper bounds] -- the same set a
+   * brute-force per-sample test of all edges yields. */
+  {
+    const int n_items = s_misc[3];
+    /* each warp owns a contiguous chunk of items and its lanes take consecutive items, so neighbouring
+     * lanes work on neighbouring rows of the same edge (same sign, same primitive, adjacent span words) */
+    const int chunk = ((n_items + nwarp - 1) / nwarp + 31) & ~31;
+    const int it_end = min((wid + 1) * chunk, n_items);
+    int it = wid * chunk + lane;
+    if (it < it_end) {
+      /* the edge holding item `it`: last edge whose offset is <= it (edges with no rows share offsets) */
+      int lo = 0, hi = nv - 1;
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (__float_as_int(vs.eaux[mid].w) <= it) lo = mid; else hi = mid - 1; }
+      int e = lo;
+      for (; it < it_end; it += 32) {
+        while (e + 1 < nv && __float_as_int(vs.eaux[e + 1].w) <= it) e++;
+        const float4 X = vs.eaux[e];
+        const float4 E = vs.edges[e];
+        const RPrim& R = vs.prims[__float_as_int(E.w)];
+        const int c0 = R.col0, c1 = R.col1;
+        const float A = E.x;
+        const int j = __float_as_int(X.z) + (it - __float_as_int(X.w));
+        const float y = (float)j + 0.5f;
+        const float t = fmaf(E.y, y, E.z);
+        uint32_t* w = reinterpret_cast<uint32_t*>(&vs.spans[R.span0 + (j - R.row0)]);
+        /* one search for both orientations: for A < 0 the column axis is mirrored (u = -i), which turns
+         * "last column that holds" into "first mirrored column that holds" */
+        const int sg = (A < 0.0f) ? -1 : 1;
+        int v;
+        if (A != 0.0f) {
+          auto ok = [&](int u) { return fmaf(A, (float)(sg * u) + 0.5f, t) >= 0.0f; };
+          const float est = fmaf(X.x, y, X.y) - 0.5f;
+          const int u = first_true(sg > 0 ? est : -est, sg > 0 ? c0 : -c1, sg > 0 ? c1 : -c0, ok);
+          v = sg * u;
+        } else {
+          v = (t >= 0.0f) ? c1 : c0 - 1; /* horizontal edge: the whole row holds or none of it */
+        }
+        /* fold into the span: low half = max of lower bounds, high half = min of upper bounds */
+        const int shift = (A > 0.0f) ? 0 : 16;
+        uint32_t old = *w;
+        for (;;) {
+          const int cur = (int)(short)(old >> shift);
+          if ((A > 0.0f) ? (cur >= v) : (cur <= v)) break;
+          const uint32_t prev = atomicCAS(w, old, (old & ~(0xFFFFu << shift)) | ((uint32_t)(uint16_t)v << shift));
+          if (prev == old) break;
+          old = prev;
+        }
+      }
+    }
   }
   __syncthreads();
   /* F: tile bins from the spans: one work item per (primitive, tile row) */
@@ -541,7 +639,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   constexpr int NV = (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESCHW4E) ? 1 : 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_off[2 * MG_MAX_PRIMS + 2];
-  __shared__ int s_misc[4];
+  __shared__ int s_misc[8];
   const int env = blockIdx.x;
   if (env >= batch) return;
   EnvState& stg = states[env];
@@ -567,6 +665,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   for (int v = 0; v < NV; v++) {
     int view = (NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1);
     build_view<SS>(vsm[v], st, sc, view, res_out, ecap, scap, s_off, s_misc);
+    if (threadIdx.x == 0) s_misc[4] = 0; /* next tile to hand out */
     __syncthreads();
   }
   const bool fresh = st.fresh != 0;
@@ -578,7 +677,14 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   const int hw_id = threadIdx.x >> 4, hl = threadIdx.x & 15;
   const int n_hw = blockDim.x >> 4;
 
-  for (int tile = hw_id; tile < RGRID * RGRID; tile += n_hw) {
+  /* tiles are handed out dynamically (flat tiles cost a fraction of busy ones) */
+  const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+  (void)hw_id; (void)n_hw;
+  for (;;) {
+    int tile = 0;
+    if (hl == 0) tile = atomicAdd(&s_misc[4], 1);
+    tile = __shfl_sync(hmask, tile, 0, 16);
+    if (tile >= RGRID * RGRID) break;
     const int tx = tile % RGRID, ty = tile / RGRID; /* ty counts GL rows (bottom-up) */
     /* per tile and view: the covering primitive, which mask words hold primitives above it, and whether
      * the whole tile is one flat colour (nothing above the cover / nothing at all) */
