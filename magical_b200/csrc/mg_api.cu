@@ -24,19 +24,20 @@
 
 cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
                               int lanes_per_env, int block_threads, cudaStream_t stream);
-cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
-                                  const TpeLayout* L, double* spill, cudaStream_t stream);
+cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int env0,
+                                  int count, const TpeLayout* L, double* spill, cudaStream_t stream);
 size_t mg_tpe_smem_bytes(const TpeLayout* L);
 size_t mg_tpe_spill_doubles_per_env(const TpeLayout* L);
-cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int batch, int auto_reset, int mode,
+cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
                              int n_scenes, uint32_t reset_seed, float* reward, uint8_t* done, float* score,
                              cudaStream_t stream);
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
                             const int32_t* scene_ids, int first_time, cudaStream_t stream);
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
-                             int res_out, int ecap, int scap, int only_fresh, cudaStream_t stream);
+                             int res_out, int ecap, int scap, int rcap, int only_fresh, int env0, int count,
+                             cudaStream_t stream);
 cudaError_t mg_raster_upload_units(const double* units);
-size_t mg_raster_smem_bytes(int mode, int ecap, int scap);
+size_t mg_raster_smem_bytes(int mode, int ecap, int scap, int rcap);
 
 struct mg_handle {
   mg_config_t cfg;
@@ -50,11 +51,18 @@ struct mg_handle {
   int res_out;
   int ecap;
   int scap;             /* span-table rows the rasteriser reserves per view */
+  int rcap;             /* window-space primitives (draw prims + expanded line segments) it reserves */
   int lanes_per_env;    /* 16: two environments share a warp in K1; 32: one warp per environment */
   int block_threads;    /* K1 block size: 512 = one phase-aligned block per SM, 128 = small blocks */
   int use_tpe;          /* K1 variant: 1 = thread per environment (mg_physics_tpe.h), 0 = lanes per environment */
   TpeLayout tpe;        /* private-word layout of the thread-per-environment kernel */
   double* d_spill;      /* its contact spill area */
+  /* mg_step software pipeline: the batch is cut into chunks whose physics and raster kernels run on two
+   * internal streams, staggered so that the raster of chunk c overlaps the physics of chunk c + 1 (the
+   * physics is latency-bound at ~13 % issue utilisation, the raster issue-bound: they share SMs well) */
+  int n_chunks;
+  cudaStream_t side[2];
+  cudaEvent_t ev_start, ev_phys[2], ev_done[2];
   int64_t launches;
 };
 
@@ -109,7 +117,7 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
 
   /* derive per-scene constants on the host */
   std::vector<DeviceScene> host(cfg->n_scenes);
-  int ecap = 64, scap = 64;
+  int ecap = 64, scap = 64, rcap = 32;
   const int ss = cfg->obs_mode == MG_OBS_RAW ? 1 : 4;
   const int res_full = res_out * ss;
   const double S_full = (double)res_full / 2.04;
@@ -154,9 +162,12 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
     if (rprims > 192) return fail(MG_E_INVALID, "mg_create: too many draw primitives in one scene%s", "");
     if (edges > ecap) ecap = edges;
     if (rows > scap) scap = rows;
+    if (rprims > rcap) rcap = rprims;
   }
   ecap = (ecap + 63) / 64 * 64;
   scap = (scap + 63) / 64 * 64;
+  if (scap < 2 * ecap) scap = 2 * ecap; /* the window-space vertices are staged inside the span table */
+  rcap = (rcap + 31) / 32 * 32;
   /* K1 serves one environment with 16 lanes when every schedule level fits (it does for all registered
    * tasks), which doubles the environments in flight per SM; MG_LANES_PER_ENV=32 forces a full warp */
   int lanes = 16;
@@ -166,7 +177,7 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
     int v = atoi(ev);
     if (v == 32 || (v == 16 && lanes == 16)) lanes = v;
   }
-  if (mg_raster_smem_bytes(cfg->obs_mode, ecap, scap) > 200 * 1024)
+  if (mg_raster_smem_bytes(cfg->obs_mode, ecap, scap, rcap) > 200 * 1024)
     return fail(MG_E_INVALID, "mg_create: scene has too many draw edges for the rasteriser's shared memory%s", "");
 
   mg_handle* h = new (std::nothrow) mg_handle();
@@ -177,6 +188,7 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   h->res_out = res_out;
   h->ecap = ecap;
   h->scap = scap;
+  h->rcap = rcap;
   h->lanes_per_env = lanes;
   /* phase-aligned 512-thread blocks need enough environments to fill the 148 SMs */
   h->block_threads = (cfg->batch / (512 / lanes) >= 2 * 148) ? 512 : 128;
@@ -221,6 +233,25 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
     mg_destroy(h);
     return fail(MG_E_NOMEM, "mg_create: cudaMalloc: %s", cudaGetErrorString(e));
   }
+  /* measured on B200 (ClusterColour, 65536 envs): 1 chunk 23.8 ms, 2: 24.0, 4: 25.7, 8: 29.1 per env-step --
+   * both kernels are shared-memory-capacity bound per SM, so co-residency costs more than the overlap
+   * gains; the pipeline stays available through MG_CHUNKS but is off by default */
+  h->n_chunks = 1;
+  if (const char* ev = getenv("MG_CHUNKS")) {
+    int v = atoi(ev);
+    if (v >= 1 && v <= 16 && h->use_tpe) h->n_chunks = v;
+  }
+  if (h->n_chunks > 1) {
+    bool ok = cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+      ok = cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_phys[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      mg_destroy(h);
+      return fail(MG_E_CUDA, "mg_create: stream / event creation failed%s", "");
+    }
+  }
   if ((e = cudaMemcpyAsync(h->d_scenes, host.data(), sizeof(DeviceScene) * (size_t)cfg->n_scenes, cudaMemcpyHostToDevice,
                            h->stream)) != cudaSuccess ||
       (e = cudaMemsetAsync(h->d_states, 0, sizeof(EnvState) * (size_t)cfg->batch, h->stream)) != cudaSuccess) {
@@ -256,6 +287,12 @@ int mg_destroy(mg_handle* h) {
   cudaFree(h->d_ids);
   cudaFree(h->d_scene_ids);
   cudaFree(h->d_spill);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  for (int i = 0; i < 2; i++) {
+    if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
+    if (h->ev_phys[i]) cudaEventDestroy(h->ev_phys[i]);
+    if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+  }
   delete h;
   return MG_OK;
 }
@@ -273,7 +310,7 @@ int64_t mg_obs_nbytes(const mg_handle* h) { return h ? h->obs_bytes : -1; }
 static int do_raster(mg_handle* h, int only_fresh) {
   if (!h->obs) return fail(MG_E_STATE, "no observation buffer bound (call mg_bind_obs first)%s", "");
   CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->cfg.batch, h->res_out, h->ecap,
-                            h->scap, only_fresh, h->stream));
+                            h->scap, h->rcap, only_fresh, 0, h->cfg.batch, h->stream));
   h->launches++;
   return MG_OK;
 }
@@ -308,19 +345,54 @@ static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_de
   if (!actions_dev) return fail(MG_E_INVALID, "mg_step: null actions%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   if (h->use_tpe)
-    CUDA_TRY(mg_launch_physics_tpe(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, &h->tpe, h->d_spill, h->stream));
+    CUDA_TRY(mg_launch_physics_tpe(h->d_states, h->d_scenes, actions_dev, 0, h->cfg.batch, &h->tpe, h->d_spill,
+                                   h->stream));
   else
     CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads,
                                h->stream));
-  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, h->cfg.auto_reset, 0, h->cfg.n_scenes,
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, h->cfg.auto_reset, 0, h->cfg.n_scenes,
                             (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->stream));
   h->launches += 2;
+  return MG_OK;
+}
+
+/* mg_step as a two-stream software pipeline over chunks of the batch (see mg_handle::n_chunks).  Order on
+ * the GPU: phys(0) | phys(1) + raster(0) | phys(2) + raster(1) | ... | raster(C-1).  Everything is fenced
+ * against the caller's stream with events, so the call stays asynchronous and stream-ordered. */
+static int step_pipelined(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev,
+                          float* score_dev) {
+  if (!actions_dev) return fail(MG_E_INVALID, "mg_step: null actions%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const int B = h->cfg.batch, C = h->n_chunks;
+  /* chunk boundaries on multiples of 32 environments (one warp of the physics kernel) */
+  const int per = ((B + C - 1) / C + 31) / 32 * 32;
+  CUDA_TRY(cudaEventRecord(h->ev_start, h->stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->side[0], h->ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(h->side[1], h->ev_start, 0));
+  for (int c = 0; c * per < B; c++) {
+    const int env0 = c * per, count = (env0 + per <= B) ? per : B - env0;
+    cudaStream_t st = h->side[c & 1];
+    /* stagger: the physics of chunk c starts when the physics of chunk c - 1 has finished */
+    if (c > 0) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_phys[(c - 1) & 1], 0));
+    CUDA_TRY(mg_launch_physics_tpe(h->d_states, h->d_scenes, actions_dev, env0, count, &h->tpe, h->d_spill, st));
+    CUDA_TRY(cudaEventRecord(h->ev_phys[c & 1], st));
+    CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, env0, count, h->cfg.auto_reset, 0, h->cfg.n_scenes,
+                              (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, st));
+    CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, B, h->res_out, h->ecap, h->scap, h->rcap,
+                              0, env0, count, st));
+    h->launches += 3;
+  }
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(cudaEventRecord(h->ev_done[i], h->side[i]));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_done[i], 0));
+  }
   return MG_OK;
 }
 
 int mg_step(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
   if (!h) return fail(MG_E_INVALID, "mg_step: null handle%s", "");
   if (!h->obs) return fail(MG_E_STATE, "mg_step: no observation buffer bound (call mg_bind_obs first)%s", "");
+  if (h->n_chunks > 1) return step_pipelined(h, actions_dev, reward_dev, done_dev, score_dev);
   int rc = do_physics(h, actions_dev, reward_dev, done_dev, score_dev);
   if (rc != MG_OK) return rc;
   return do_raster(h, 0);
@@ -340,7 +412,7 @@ int mg_render(mg_handle* h) {
 int mg_score(mg_handle* h, float* score_dev) {
   if (!h || !score_dev) return fail(MG_E_INVALID, "mg_score: null argument%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, h->cfg.batch, 0, 1, 1, 0u, nullptr, nullptr, score_dev, h->stream));
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, 0, 1, 1, 0u, nullptr, nullptr, score_dev, h->stream));
   h->launches++;
   return MG_OK;
 }

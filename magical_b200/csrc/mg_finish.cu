@@ -236,11 +236,12 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) { /* lowbias32 integer has
   return x;
 }
 
-__global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, int batch,
+__global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, int env0, int count,
                          int auto_reset, int mode, int n_scenes, uint32_t reset_seed, float* __restrict__ reward,
                          uint8_t* __restrict__ done, float* __restrict__ score) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= batch) return;
+  if (env >= count) return;
+  env += env0; /* this launch covers environments [env0, env0 + count) */
   EnvState& st = states[env];
   const DeviceScene* ds = scenes + st.scene;
   const mg_scene_t& sc = ds->s;
@@ -294,12 +295,12 @@ __global__ void k_reset(EnvState* __restrict__ states, const DeviceScene* __rest
   }
 }
 
-cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int batch, int auto_reset, int mode,
+cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
                              int n_scenes, uint32_t reset_seed, float* reward, uint8_t* done, float* score,
                              cudaStream_t stream) {
   int threads = 128;
-  k_finish<<<(batch + threads - 1) / threads, threads, 0, stream>>>(states, scenes, batch, auto_reset, mode, n_scenes,
-                                                                    reset_seed, reward, done, score);
+  k_finish<<<(count + threads - 1) / threads, threads, 0, stream>>>(states, scenes, env0, count, auto_reset, mode,
+                                                                    n_scenes, reset_seed, reward, done, score);
   return cudaGetLastError();
 }
 

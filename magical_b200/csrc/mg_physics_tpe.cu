@@ -14,9 +14,10 @@
 
 __global__ void __launch_bounds__(TPE_THREADS)
 k_physics_tpe(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, const int32_t* __restrict__ actions,
-              int batch, TpeLayout L, double* __restrict__ spill) {
+              int env0, int count, TpeLayout L, double* __restrict__ spill) {
   extern __shared__ __align__(16) double tpe_words[];
-  int env = blockIdx.x * TPE_THREADS + threadIdx.x;
+  int env = env0 + blockIdx.x * TPE_THREADS + threadIdx.x;
+  const int batch = env0 + count; /* this launch covers environments [env0, env0 + count) */
   /* lanes beyond the batch keep their warp complete for the cooperative narrowphase (they do no work of
    * their own and store nothing) */
   const bool live = env < batch;
@@ -37,8 +38,8 @@ k_physics_tpe(EnvState* __restrict__ states, const DeviceScene* __restrict__ sce
 size_t mg_tpe_smem_bytes(const TpeLayout* L) { return (size_t)L->words * sizeof(double) * TPE_THREADS; }
 size_t mg_tpe_spill_doubles_per_env(const TpeLayout* L) { return (size_t)(TPE_MAX_CONTACTS - L->kcon) * TPE_CON_WORDS; }
 
-cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
-                                  const TpeLayout* L, double* spill, cudaStream_t stream) {
+cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int env0,
+                                  int count, const TpeLayout* L, double* spill, cudaStream_t stream) {
   const size_t smem = mg_tpe_smem_bytes(L);
   static size_t configured = 0;
   if (configured < smem) {
@@ -48,7 +49,7 @@ cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, c
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  k_physics_tpe<<<(batch + TPE_THREADS - 1) / TPE_THREADS, TPE_THREADS, smem, stream>>>(states, scenes, actions, batch, *L,
-                                                                                      spill);
+  k_physics_tpe<<<(count + TPE_THREADS - 1) / TPE_THREADS, TPE_THREADS, smem, stream>>>(states, scenes, actions, env0,
+                                                                                      count, *L, spill);
   return cudaGetLastError();
 }

@@ -39,6 +39,7 @@
 #define RGRID 12           /* tiles per side */
 #define RMAXP 192          /* window-space primitives (draw prims + expanded line segments) */
 #define RWORDS (RMAXP / 32)
+#define RSHORT 12          /* polygon edges bounding fewer rows than this are processed one edge per lane */
 #define BG_R 231
 #define BG_G 231
 #define BG_B 234
@@ -121,12 +122,13 @@ __device__ __forceinline__ float2 prim_vertex(const EnvState& st, const mg_scene
 }
 
 struct ViewSmem {
-  RPrim* prims;     /* [RMAXP] */
-  float4* edges;    /* [ecap + 2*RMAXP]  (A, B, C, -) ; line segments: 2 float4 behind the pool */
+  int rcap, rwords; /* capacity in window-space primitives (multiple of 32, <= RMAXP) and mask words per tile */
+  RPrim* prims;     /* [rcap] */
+  float4* edges;    /* [ecap + 2*rcap]  (A, B, C, prim | rows << 8) ; line segments: 2 float4 behind the pool */
   float4* eaux;     /* [ecap] per edge: (m, q, ymin, ymax) with boundary x*(y) = m*y + q */
-  float2* verts;    /* [ecap] */
+  float2* verts;    /* [ecap]; dead once the edge equations exist, so it lives inside the span table */
   short2* spans;    /* [scap] (lo, hi) per (primitive, row) */
-  uint32_t* tiles;  /* [RGRID*RGRID*RWORDS] */
+  uint32_t* tiles;  /* [RGRID*RGRID*rwords] */
   int32_t* cover;   /* [RGRID*RGRID] top-most primitive covering the whole tile, -1 = none */
 };
 
@@ -255,10 +257,10 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     if (tid == 0) {
       s_off[np] = off;
       s_misc[0] = off > ecap ? ecap : off;
-      s_misc[1] = rp > RMAXP ? RMAXP : rp;
+      s_misc[1] = rp > vs.rcap ? vs.rcap : rp;
     }
   }
-  for (int i = tid; i < RGRID * RGRID * RWORDS; i += nt) vs.tiles[i] = 0u;
+  for (int i = tid; i < RGRID * RGRID * vs.rwords; i += nt) vs.tiles[i] = 0u;
   for (int i = tid; i < RGRID * RGRID; i += nt) vs.cover[i] = -1;
   __syncthreads();
   const int nv = s_misc[0];
@@ -284,7 +286,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         float2 a = vs.verts[v0 + k], b = vs.verts[v0 + (k + 1) % n];
         float dx = b.x - a.x, dy = b.y - a.y;
         float L = sqrtf(fmaf(dx, dx, dy * dy));
-        if (rp0 + k < RMAXP) {
+        if (rp0 + k < vs.rcap) {
           /* a segment's two float4 (ax, ay, ux, uy), (L, s0, hw, stipple) live behind the edge pool */
           RPrim& R = vs.prims[rp0 + k];
           const int slot = ecap + 2 * (rp0 + k);
@@ -308,7 +310,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         }
         s0 += L;
       }
-    } else if (rp0 < RMAXP) {
+    } else if (rp0 < vs.rcap) {
       RPrim& R = vs.prims[rp0];
       float area2 = 0.0f;
       float l = INFINITY, r = -INFINITY, b = INFINITY, t = -INFINITY;
@@ -366,8 +368,9 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= v) lo = mid; else hi = mid - 1; }
     const mg_prim_t& pr = sc.prims[lo];
     int rp0 = s_off[MG_MAX_PRIMS + 1 + lo];
-    if (pr.kind == MG_PRIM_LINELOOP || rp0 >= RMAXP) {
+    if (pr.kind == MG_PRIM_LINELOOP || rp0 >= vs.rcap) {
       vs.eaux[v] = make_float4(0.0f, 0.0f, __int_as_float(0), __int_as_float(0));
+      vs.edges[v] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
       continue;
     }
     int v0 = s_off[lo], n = pr.nvert, k = v - v0;
@@ -377,7 +380,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     float A = a.y - b.y, B = b.x - a.x;
     float C = -fmaf(A, a.x, B * a.y);
     A *= sgn; B *= sgn; C *= sgn;
-    vs.edges[v] = make_float4(A, B, C, __int_as_float(rp0));
+
     /* boundary column of this edge on row y: x*(y) = -(B y + C)/A = m y + q (an ESTIMATE only) */
     float inv = (A != 0.0f) ? __fdividef(1.0f, A) : 0.0f;
     /* rows with  ymin_e - 1 <= j + 0.5 <= ymax_e + 1  (decided with the exact fp32 comparisons), clipped
@@ -393,7 +396,10 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     while (r1 >= r0 && (float)r1 + 0.5f > R.ymax + 0.01f) r1--;
     j0 = max(j0, r0); j1 = min(j1, r1);
     const int cnt = j1 >= j0 ? j1 - j0 + 1 : 0;
-    vs.eaux[v] = make_float4(-B * inv, -C * inv, __int_as_float(j0), __int_as_float(cnt));
+    /* edges.w = primitive | rows << 8;  eaux.w = rows that enter the item queue (long edges only: the
+     * short ones -- the sides of the many-gons -- are handled one edge per lane) */
+    vs.edges[v] = make_float4(A, B, C, __int_as_float(rp0 | (cnt << 8)));
+    vs.eaux[v] = make_float4(-B * inv, -C * inv, __int_as_float(j0), __int_as_float(cnt >= RSHORT ? cnt : 0));
   }
   __syncthreads();
   /* E0: warp 0 turns the per-edge row counts into offsets (exclusive prefix) while the other warps
@@ -438,51 +444,62 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
    * so the covered set of a row is [max of the lower bounds, min of the upper bounds] -- the same set a
    * brute-force per-sample test of all edges yields. */
   {
+    /* fold the bound of edge (E, X) on sample row j into that row's span */
+    auto fold = [&](const float4& E, const float4& X, int j) {
+      const RPrim& R = vs.prims[__float_as_int(E.w) & 0xFF];
+      const int c0 = R.col0, c1 = R.col1;
+      const float A = E.x;
+      const float y = (float)j + 0.5f;
+      const float t = fmaf(E.y, y, E.z);
+      uint32_t* w = reinterpret_cast<uint32_t*>(&vs.spans[R.span0 + (j - R.row0)]);
+      /* one search for both orientations: for A < 0 the column axis is mirrored (u = -i), which turns
+       * "last column that holds" into "first mirrored column that holds" */
+      const int sg = (A < 0.0f) ? -1 : 1;
+      int v;
+      if (A != 0.0f) {
+        auto ok = [&](int u) { return fmaf(A, (float)(sg * u) + 0.5f, t) >= 0.0f; };
+        const float est = fmaf(X.x, y, X.y) - 0.5f;
+        const int u = first_true(sg > 0 ? est : -est, sg > 0 ? c0 : -c1, sg > 0 ? c1 : -c0, ok);
+        v = sg * u;
+      } else {
+        v = (t >= 0.0f) ? c1 : c0 - 1; /* horizontal edge: the whole row holds or none of it */
+      }
+      /* low half = max of lower bounds, high half = min of upper bounds */
+      const int shift = (A > 0.0f) ? 0 : 16;
+      uint32_t old = *w;
+      for (;;) {
+        const int cur = (int)(short)(old >> shift);
+        if ((A > 0.0f) ? (cur >= v) : (cur <= v)) break;
+        const uint32_t prev = atomicCAS(w, old, (old & ~(0xFFFFu << shift)) | ((uint32_t)(uint16_t)v << shift));
+        if (prev == old) break;
+        old = prev;
+      }
+    };
+    /* long edges: each warp owns a contiguous chunk of (edge, row) items and its lanes take consecutive
+     * items, so neighbouring lanes work on neighbouring rows of the same edge */
     const int n_items = s_misc[3];
-    /* each warp owns a contiguous chunk of items and its lanes take consecutive items, so neighbouring
-     * lanes work on neighbouring rows of the same edge (same sign, same primitive, adjacent span words) */
     const int chunk = ((n_items + nwarp - 1) / nwarp + 31) & ~31;
     const int it_end = min((wid + 1) * chunk, n_items);
     int it = wid * chunk + lane;
     if (it < it_end) {
-      /* the edge holding item `it`: last edge whose offset is <= it (edges with no rows share offsets) */
+      /* the edge holding item `it`: last edge whose offset is <= it (edges with no items share offsets) */
       int lo = 0, hi = nv - 1;
       while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (__float_as_int(vs.eaux[mid].w) <= it) lo = mid; else hi = mid - 1; }
       int e = lo;
       for (; it < it_end; it += 32) {
         while (e + 1 < nv && __float_as_int(vs.eaux[e + 1].w) <= it) e++;
         const float4 X = vs.eaux[e];
-        const float4 E = vs.edges[e];
-        const RPrim& R = vs.prims[__float_as_int(E.w)];
-        const int c0 = R.col0, c1 = R.col1;
-        const float A = E.x;
-        const int j = __float_as_int(X.z) + (it - __float_as_int(X.w));
-        const float y = (float)j + 0.5f;
-        const float t = fmaf(E.y, y, E.z);
-        uint32_t* w = reinterpret_cast<uint32_t*>(&vs.spans[R.span0 + (j - R.row0)]);
-        /* one search for both orientations: for A < 0 the column axis is mirrored (u = -i), which turns
-         * "last column that holds" into "first mirrored column that holds" */
-        const int sg = (A < 0.0f) ? -1 : 1;
-        int v;
-        if (A != 0.0f) {
-          auto ok = [&](int u) { return fmaf(A, (float)(sg * u) + 0.5f, t) >= 0.0f; };
-          const float est = fmaf(X.x, y, X.y) - 0.5f;
-          const int u = first_true(sg > 0 ? est : -est, sg > 0 ? c0 : -c1, sg > 0 ? c1 : -c0, ok);
-          v = sg * u;
-        } else {
-          v = (t >= 0.0f) ? c1 : c0 - 1; /* horizontal edge: the whole row holds or none of it */
-        }
-        /* fold into the span: low half = max of lower bounds, high half = min of upper bounds */
-        const int shift = (A > 0.0f) ? 0 : 16;
-        uint32_t old = *w;
-        for (;;) {
-          const int cur = (int)(short)(old >> shift);
-          if ((A > 0.0f) ? (cur >= v) : (cur <= v)) break;
-          const uint32_t prev = atomicCAS(w, old, (old & ~(0xFFFFu << shift)) | ((uint32_t)(uint16_t)v << shift));
-          if (prev == old) break;
-          old = prev;
-        }
+        fold(vs.edges[e], X, __float_as_int(X.z) + (it - __float_as_int(X.w)));
       }
+    }
+    /* short edges: one edge per lane, a handful of rows each */
+    for (int v = tid; v < nv; v += nt) {
+      const float4 E = vs.edges[v];
+      const int cnt = __float_as_int(E.w) >> 8;
+      if (cnt <= 0 || cnt >= RSHORT) continue;
+      const float4 X = vs.eaux[v];
+      const int j0 = __float_as_int(X.z);
+      for (int r = 0; r < cnt; r++) fold(E, X, j0 + r);
     }
   }
   __syncthreads();
@@ -510,7 +527,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     if (umax < umin) continue;
     const bool solid = (R.rgb >> 24) == 0; /* stippled segments never cover a tile completely */
     for (int tx = umin / TS; tx <= umax / TS && tx < RGRID; tx++) {
-      atomicOr(&vs.tiles[(ty * RGRID + tx) * RWORDS + (p >> 5)], 1u << (p & 31));
+      atomicOr(&vs.tiles[(ty * RGRID + tx) * vs.rwords + (p >> 5)], 1u << (p & 31));
       if (all_rows && solid && cmin <= tx * TS && cmax >= tx * TS + TS - 1) atomicMax(&vs.cover[ty * RGRID + tx], p);
     }
   }
@@ -537,7 +554,7 @@ __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int t
   constexpr uint32_t FULLM = (SS == 4) ? 0xFFFFu : 1u;
   uint32_t unres[4] = {FULLM, FULLM, FULLM, FULLM};
   uint32_t sr[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-  const uint32_t* tm = vs.tiles + tile * RWORDS;
+  const uint32_t* tm = vs.tiles + tile * vs.rwords;
   const int x0 = X0 * SS, y0 = Yg * SS;
   uint32_t any = FULLM;
   while (words && any) {
@@ -634,13 +651,13 @@ __device__ __forceinline__ void stack_push(uint32_t* w, uint32_t n, bool fresh) 
 template <int MODE>
 __global__ void __launch_bounds__(256, RASTER_MIN_BLOCKS)
 k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, uint8_t* __restrict__ obs, int batch,
-         int res_out, int ecap, int scap, int only_fresh) {
+         int res_out, int ecap, int scap, int rcap, int only_fresh, int env0) {
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
   constexpr int NV = (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESCHW4E) ? 1 : 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_off[2 * MG_MAX_PRIMS + 2];
   __shared__ int s_misc[8];
-  const int env = blockIdx.x;
+  const int env = env0 + blockIdx.x; /* this launch covers environments [env0, env0 + gridDim.x) */
   if (env >= batch) return;
   EnvState& stg = states[env];
   const EnvState& st = stg;
@@ -653,12 +670,14 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   {
     unsigned char* p = smem_raw;
     for (int v = 0; v < NV; v++) {
-      vsm[v].edges = reinterpret_cast<float4*>(p); p += sizeof(float4) * (size_t)(ecap + 2 * RMAXP);
+      vsm[v].rcap = rcap; vsm[v].rwords = rcap >> 5;
+      vsm[v].edges = reinterpret_cast<float4*>(p); p += sizeof(float4) * (size_t)(ecap + 2 * rcap);
       vsm[v].eaux = reinterpret_cast<float4*>(p); p += sizeof(float4) * (size_t)ecap;
-      vsm[v].verts = reinterpret_cast<float2*>(p); p += sizeof(float2) * (size_t)ecap;
-      vsm[v].prims = reinterpret_cast<RPrim*>(p); p += sizeof(RPrim) * RMAXP;
-      vsm[v].spans = reinterpret_cast<short2*>(p); p += sizeof(short2) * (size_t)scap;
-      vsm[v].tiles = reinterpret_cast<uint32_t*>(p); p += sizeof(uint32_t) * RGRID * RGRID * RWORDS;
+      vsm[v].prims = reinterpret_cast<RPrim*>(p); p += sizeof(RPrim) * (size_t)rcap;
+      vsm[v].spans = reinterpret_cast<short2*>(p);
+      vsm[v].verts = reinterpret_cast<float2*>(p); /* scap * 4 >= ecap * 8 (host) */
+      p += sizeof(short2) * (size_t)scap;
+      vsm[v].tiles = reinterpret_cast<uint32_t*>(p); p += sizeof(uint32_t) * RGRID * RGRID * (size_t)(rcap >> 5);
       vsm[v].cover = reinterpret_cast<int32_t*>(p); p += sizeof(int32_t) * RGRID * RGRID;
     }
   }
@@ -694,9 +713,9 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
 #pragma unroll
     for (int v = 0; v < NV; v++) {
       cover[v] = vsm[v].cover[tile];
-      const uint32_t* tm = vsm[v].tiles + tile * RWORDS;
+      const uint32_t* tm = vsm[v].tiles + tile * vsm[v].rwords;
       uint32_t wm = 0u, above = 0u;
-      for (int w = 0; w < RWORDS; w++) {
+      for (int w = 0; w < vsm[v].rwords; w++) {
         uint32_t bits = tm[w];
         if (cover[v] >= 0) {
           if ((cover[v] >> 5) > w) bits = 0u;
@@ -820,10 +839,10 @@ static int n_views(int mode) {
   return (mode == MG_OBS_LORES4E || mode == MG_OBS_LORES4A || mode == MG_OBS_LORESCHW4E) ? 1 : 2;
 }
 
-size_t mg_raster_smem_bytes(int mode, int ecap, int scap) {
-  size_t per_view = sizeof(float4) * (size_t)(ecap + 2 * RMAXP) + sizeof(float4) * (size_t)ecap +
-                    sizeof(float2) * (size_t)ecap + sizeof(RPrim) * RMAXP +
-                    sizeof(short2) * (size_t)scap + sizeof(uint32_t) * RGRID * RGRID * RWORDS +
+size_t mg_raster_smem_bytes(int mode, int ecap, int scap, int rcap) {
+  size_t per_view = sizeof(float4) * (size_t)(ecap + 2 * rcap) + sizeof(float4) * (size_t)ecap +
+                    sizeof(RPrim) * (size_t)rcap +
+                    sizeof(short2) * (size_t)scap + sizeof(uint32_t) * RGRID * RGRID * (size_t)(rcap >> 5) +
                     sizeof(int32_t) * RGRID * RGRID;
   return per_view * n_views(mode);
 }
@@ -834,25 +853,27 @@ cudaError_t mg_raster_upload_units(const double* units /* [130][2] */) {
 
 template <int MODE>
 static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch, int res_out,
-                               int ecap, int scap, int only_fresh, cudaStream_t stream) {
-  size_t smem = mg_raster_smem_bytes(MODE, ecap, scap);
+                               int ecap, int scap, int rcap, int only_fresh, int env0, int count,
+                               cudaStream_t stream) {
+  size_t smem = mg_raster_smem_bytes(MODE, ecap, scap, rcap);
   cudaError_t e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  k_raster<MODE><<<batch, 256, smem, stream>>>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh);
+  k_raster<MODE><<<count, 256, smem, stream>>>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0);
   return cudaGetLastError();
 }
 
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
-                             int res_out, int ecap, int scap, int only_fresh, cudaStream_t stream) {
+                             int res_out, int ecap, int scap, int rcap, int only_fresh, int env0, int count,
+                             cudaStream_t stream) {
   switch (mode) {
-    case MG_OBS_LORES4E: return launch_mode<MG_OBS_LORES4E>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
-    case MG_OBS_LORES4A: return launch_mode<MG_OBS_LORES4A>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
-    case MG_OBS_LORES3EA: return launch_mode<MG_OBS_LORES3EA>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
-    case MG_OBS_LORESSTACK: return launch_mode<MG_OBS_LORESSTACK>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
-    case MG_OBS_LORESCHW4E: return launch_mode<MG_OBS_LORESCHW4E>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
-    case MG_OBS_RAW: return launch_mode<MG_OBS_RAW>(states, scenes, obs, batch, res_out, ecap, scap, only_fresh, stream);
+    case MG_OBS_LORES4E: return launch_mode<MG_OBS_LORES4E>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
+    case MG_OBS_LORES4A: return launch_mode<MG_OBS_LORES4A>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
+    case MG_OBS_LORES3EA: return launch_mode<MG_OBS_LORES3EA>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
+    case MG_OBS_LORESSTACK: return launch_mode<MG_OBS_LORESSTACK>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
+    case MG_OBS_LORESCHW4E: return launch_mode<MG_OBS_LORESCHW4E>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
+    case MG_OBS_RAW: return launch_mode<MG_OBS_RAW>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
   }
   return cudaErrorInvalidValue;
 }

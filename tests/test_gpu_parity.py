@@ -291,3 +291,34 @@ def test_auto_reset_redraws_scene_from_pool(built):
     assert len(set(scenes)) > 2
     assert int(venv.get_state(5)['episode_steps']) == 1
     venv.close()
+
+
+def test_pipelined_step_equals_single_stream(built, monkeypatch):
+    """mg_step's two-stream chunk pipeline (physics of chunk c+1 overlapping
+    the raster of chunk c) must produce exactly what the single-stream
+    sequence produces."""
+    import torch
+    import magical_b200 as magical
+    batch = 100
+    rng = np.random.RandomState(5)
+    acts = rng.randint(0, 18, size=(45, batch)).astype(np.int32)
+    outs = []
+    for chunks in ('1', '3'):
+        monkeypatch.setenv('MG_CHUNKS', chunks)
+        venv = magical.make_vec('MoveToRegion-Demo-LoRes4E-v0', batch,
+                                auto_reset=True)
+        venv.reset()
+        dones = []
+        for t in range(45):
+            obs, rew, done, info = venv.step(torch.from_numpy(acts[t]).cuda())
+            dones.append(done.cpu().numpy().copy())
+        states = [venv.get_state(e)['pos'].copy() for e in (0, 63, 64, 99)]
+        outs.append((obs.cpu().numpy().copy(), np.stack(dones),
+                     info['eval_score'].cpu().numpy().copy(), states))
+        venv.close()
+    a, b = outs
+    assert np.array_equal(a[0], b[0])
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2])
+    for x, y in zip(a[3], b[3]):
+        assert np.array_equal(x, y)
