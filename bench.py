@@ -304,7 +304,7 @@ def run_b200(args, env_id, batch):
     rast_ms = time_loop(lambda i: venv.render(), n_k)
     peak, peak_kind = peaks()
     if phys_ms >= rast_ms:
-        kname, kms = 'k_physics (+k_finish)', phys_ms
+        kname, kms = 'k_physics_tpe (+k_finish)', phys_ms
         alg = (STATE_RW + SCALARS) * batch
     else:
         kname, kms = 'k_raster', rast_ms
@@ -314,7 +314,9 @@ def run_b200(args, env_id, batch):
         'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak,
         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
         'peak_source': peak_kind,
-        'kernel_ms': {'k_physics+k_finish': phys_ms, 'k_raster': rast_ms},
+        'kernel_ms': {'k_physics_tpe+k_finish': phys_ms, 'k_raster': rast_ms},
+        'algorithmic_bytes_per_launch': alg,
+        'physics_achieved_gbs': (STATE_RW + SCALARS) * batch / (phys_ms / 1000.0) / 1e9,
         'whole_step_achieved_gbs': BYTES_PER_STEP_TOTAL * batch / ((ms_total / K) / 1000.0) / 1e9,
         'raster_achieved_gbs': (OBS_WRITE + STACK_READ) * batch / (rast_ms / 1000.0) / 1e9,
         'note': 'the path is instruction-issue / dependent-latency bound (fp64 '
@@ -324,7 +326,12 @@ def run_b200(args, env_id, batch):
     if os.path.exists(traffic_file):
         try:
             with open(traffic_file) as fh:
-                roofline['traffic'] = json.load(fh).get(kname.split(' ')[0])
+                tr = json.load(fh)
+            # measured at the default workload's batch; scale per environment for other batches
+            per_env = tr.get(kname.split(' ')[0])
+            if per_env is not None:
+                roofline['traffic'] = per_env / tr.get('_batch', batch) * batch
+                roofline['traffic_source'] = tr.get('_source')
         except Exception:  # noqa: BLE001
             pass
 

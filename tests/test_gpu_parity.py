@@ -322,3 +322,46 @@ def test_pipelined_step_equals_single_stream(built, monkeypatch):
     assert np.array_equal(a[2], b[2])
     for x, y in zip(a[3], b[3]):
         assert np.array_equal(x, y)
+
+
+def test_mixed_task_batch_scores_match_oracle(built):
+    """BASELINE config 5 in miniature: one batch holding all 8 Demo tasks
+    (scene pool of 8, env i plays task i mod 8); random rollouts past every
+    episode end; done masks, end-of-episode scores and final poses equal the
+    oracle's for every task."""
+    import torch
+    from magical_b200.vec_env import MagicalVecEnv
+    from oracle_lib import OracleEnv
+    names = TASKS
+    tasks = [make_demo_task(n) for n in names]
+    scenes = [t.build_scene() for t in tasks]
+    batch = 40
+    venv = MagicalVecEnv(tasks[0], batch, preproc='LoRes4E', auto_reset=False,
+                         scenes=scenes)
+    scene_ids = np.arange(batch) % len(scenes)
+    venv.reset(scene_ids=scene_ids)
+    watch = list(range(8, 16))  # one env per task
+    oracles = {e: OracleEnv(scenes[scene_ids[e]], det_sincos=True)
+               for e in watch}
+    rng = np.random.RandomState(21)
+    n_steps = 245
+    seen_done = set()
+    for t in range(n_steps):
+        acts = rng.randint(0, 18, size=batch).astype(np.int32)
+        obs, rew, done, info = venv.step(torch.from_numpy(acts).cuda())
+        done_h = done.cpu().numpy()
+        score_h = info['eval_score'].cpu().numpy()
+        for e, orc in oracles.items():
+            _, o_done, o_score = orc.step(int(acts[e]))
+            assert bool(done_h[e]) == o_done, (names[scene_ids[e]], t)
+            assert np.float32(score_h[e]) == np.float32(o_score), \
+                (names[scene_ids[e]], t, score_h[e], o_score)
+            if o_done:
+                seen_done.add(names[scene_ids[e]])
+    assert seen_done == set(names)
+    for e, orc in oracles.items():
+        st, ost = venv.get_state(e), orc.state()
+        nb = int(st['n_bodies'])
+        assert int(st['overflow']) == 0
+        assert np.array_equal(st['pos'][:nb], ost['pos'][:nb]), names[scene_ids[e]]
+    venv.close()
