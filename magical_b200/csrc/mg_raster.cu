@@ -44,6 +44,9 @@
 #define BG_G 231
 #define BG_B 234
 #define ZOOM 1.02
+#ifndef RASTER_THREADS
+#define RASTER_THREADS 256
+#endif
 #ifndef RASTER_MIN_BLOCKS
 #define RASTER_MIN_BLOCKS 4
 #endif
@@ -649,7 +652,7 @@ __device__ __forceinline__ void stack_push(uint32_t* w, uint32_t n, bool fresh) 
 /* ------------------------------------------------------------------ kernel
  * MODE: MG_OBS_*;  SS: samples per output pixel side (4 for the LoRes modes, 1 for RAW). */
 template <int MODE>
-__global__ void __launch_bounds__(256, RASTER_MIN_BLOCKS)
+__global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_BLOCKS)
 k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, uint8_t* __restrict__ obs, int batch,
          int res_out, int ecap, int scap, int rcap, int only_fresh, int env0) {
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
@@ -860,7 +863,7 @@ static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  k_raster<MODE><<<count, 256, smem, stream>>>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0);
+  k_raster<MODE><<<count, RASTER_THREADS, smem, stream>>>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0);
   return cudaGetLastError();
 }
 
