@@ -173,6 +173,8 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   int lanes = 16;
   for (int i = 0; i < cfg->n_scenes; i++)
     if (host[i].aux.max_per_level > 16) lanes = 32;
+  /* the cooperative fallback kernel pairs two environments per warp only when they run the same scene */
+  if (cfg->n_scenes > 1) lanes = 32;
   if (const char* ev = getenv("MG_LANES_PER_ENV")) {
     int v = atoi(ev);
     if (v == 32 || (v == 16 && lanes == 16)) lanes = v;
@@ -191,7 +193,7 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   h->rcap = rcap;
   h->lanes_per_env = lanes;
   /* phase-aligned 512-thread blocks need enough environments to fill the 148 SMs */
-  h->block_threads = (cfg->batch / (512 / lanes) >= 2 * 148) ? 512 : 128;
+  h->block_threads = (cfg->n_scenes == 1 && cfg->batch / (512 / lanes) >= 2 * 148) ? 512 : 128;
   if (const char* ev = getenv("MG_BLOCK_THREADS")) {
     int v = atoi(ev);
     if (v == 128 || v == 512) h->block_threads = v;
