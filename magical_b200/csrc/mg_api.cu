@@ -213,6 +213,12 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   if (const char* ev = getenv("MG_PHYSICS")) {
     if (!strcmp(ev, "warp")) h->use_tpe = 0;
   }
+  if (!h->use_tpe && cfg->n_scenes > 1) {
+    /* the cooperative fallback kernel is validated for one shared scene only */
+    delete h;
+    return fail(MG_E_INVALID, "mg_create: scene pools need scenes with MAGICAL's canonical structure "
+                              "(thread-per-environment kernel)%s", "");
+  }
   if (h->use_tpe) {
     int kcon = 5;
     if (const char* ev = getenv("MG_TPE_KCON")) kcon = atoi(ev);

@@ -110,7 +110,7 @@ static inline TpeLayout tpe_make_layout(int nslots, int nblocks, int ncgroups, i
   L.off_path = L.off_bj + nblocks * 4;
   L.off_con = L.off_path + (nslots + 1) / 2;
   int con_words = kcon * TPE_CON_WORDS;
-  if (con_words < ncgroups * 2) con_words = ncgroups * 2; /* float4 group boxes share the contact words */
+  if (con_words < ncgroups * 3) con_words = ncgroups * 3; /* group boxes + info share the contact words */
   L.kcon = con_words / TPE_CON_WORDS;
   if (L.kcon > TPE_MAX_CONTACTS) L.kcon = TPE_MAX_CONTACTS;
   L.off_it = L.off_con + con_words;
@@ -135,7 +135,9 @@ struct Tpe {
   MG_HDM double& PR(int s, int k) const { return wd[(L.off_pr + s * 5 + k) * S]; } /* x y angle cos sin */
   MG_HDM double& BJ(int b, int k) const { return wd[(L.off_bj + b * 4 + k) * S]; } /* pivot x,y  gear  gear bias */
   MG_HDM float& path(int s) const { return wf[(L.off_path * 2 + s) * S]; }
-  MG_HDM float& gbb(int g, int k) const { return wf[(L.off_con * 2 + g * 4 + k) * S]; }
+  /* group box l, b, r, t (k = 0..3) and, at k = 4, shape0 | nshape << 8 | slot << 16 of the group */
+  MG_HDM float& gbb(int g, int k) const { return wf[(L.off_con * 2 + g * 6 + k) * S]; }
+  MG_HDM uint32_t& ginfo(int g) const { return reinterpret_cast<uint32_t*>(wf)[(L.off_con * 2 + g * 6 + 4) * S]; }
   MG_HDM uint32_t& IT(int k) const { return reinterpret_cast<uint32_t*>(wf)[(L.off_it * 2 + k) * S]; }
   MG_HDM uint16_t& SEP(int p) const { return wh[(L.off_sep * 4 + p) * S]; }
   MG_HDM int slot(int body) const { /* body index or <0 / MG_MAX_BODIES for the static body */
@@ -595,6 +597,8 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
         }
       }
       T.gbb(g, 0) = l; T.gbb(g, 1) = b; T.gbb(g, 2) = r; T.gbb(g, 3) = t;
+      T.ginfo(g) = (uint32_t)sc.cgroups[g].shape0 | ((uint32_t)sc.cgroups[g].nshape << 8) |
+                   ((uint32_t)T.slot(gbody) << 16);
     }
 
     /* ---- broadphase (own environment): canonical pair list -> work items for the exact narrowphase.
@@ -610,18 +614,17 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
             T.gbb(gb, 1) <= T.gbb(ga, 3)))
         continue;
       TPE_STAT(3);
-      const int sla = T.slot(sc.cgroups[ga].body), slb = T.slot(sc.cgroups[gb].body);
-      const float travelled = tpe_fadd_ru(T.path(sla), T.path(slb));
+      const uint32_t ia_ = T.ginfo(ga), ib_ = T.ginfo(gb);
+      const float travelled = tpe_fadd_ru(T.path((int)(ia_ >> 16)), T.path((int)(ib_ >> 16)));
       if (travelled < tpe_sep_get(T, p)) { TPE_STAT(4); continue; }
-      const int sa0 = sc.cgroups[ga].shape0, na = sc.cgroups[ga].nshape;
-      const int sb0 = sc.cgroups[gb].shape0, nbs = sc.cgroups[gb].nshape;
+      const int sa0 = (int)(ia_ & 0xFFu), na = (int)((ia_ >> 8) & 0xFFu);
+      const int sb0 = (int)(ib_ & 0xFFu), nbs = (int)((ib_ >> 8) & 0xFFu);
       const int first_item = n_items;
       for (int i = 0; i < na && !truncated; i++)
         for (int k = 0; k < nbs; k++) {
           if (n_items == T.L.nitems) { truncated = true; res_p = p; res_i = i; res_k = k; break; }
-          int ia = sa0 + i, ib = sb0 + k;
-          if (sc.shapes[ia].kind > sc.shapes[ib].kind) { int t = ia; ia = ib; ib = t; }
-          T.IT(n_items++) = (uint32_t)(ia | (ib << 8) | (p << 16));
+          /* (the executing lane orders the two shapes by kind, as cpCollide does, in stage A) */
+          T.IT(n_items++) = (uint32_t)((sa0 + i) | ((sb0 + k) << 8) | (p << 16));
           TPE_STAT(1);
         }
       /* LAST = settle the pair's separation after this item; CONT = the pair continues in the serial tail */
@@ -695,9 +698,15 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
           To.static_slot = tpe_shfl<S>(T.static_slot, owner);
           const DeviceScene* dso = (const DeviceScene*)tpe_shfl64<S>((uint64_t)ds, owner);
           if (j < n_all) {
-            const uint32_t it = To.IT(j - oexcl);
-            const double gap = tpe_pair_gap(To, dso, (int)(it & 0xFFu), (int)((it >> 8) & 0xFFu));
-            if (gap > 0.0) To.IT(j - oexcl) = it | ((uint32_t)tpe_level(gap) << 26);
+            uint32_t it = To.IT(j - oexcl);
+            int ia = (int)(it & 0xFFu), ib = (int)((it >> 8) & 0xFFu);
+            if (dso->s.shapes[ia].kind > dso->s.shapes[ib].kind) { /* Chipmunk's type order */
+              const int t = ia; ia = ib; ib = t;
+              it = (it & 0xFFFF0000u) | (uint32_t)ia | ((uint32_t)ib << 8);
+            }
+            const double gap = tpe_pair_gap(To, dso, ia, ib);
+            if (gap > 0.0) it |= (uint32_t)tpe_level(gap) << 26;
+            To.IT(j - oexcl) = it;
           }
         }
         tpe_sync<S>();
@@ -1021,26 +1030,37 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
         TPE_APPLY(V, sb_, c_mb, c_ib, jx, jy, c_r2x, c_r2y);
         C[9] = c_jn; C[10] = c_jt; C[11] = c_jb;
       }
-      /* blocks: force-capped pivot + gear against the static body (entities.py:703-711) */
-      for (int k = 0; k < nblk; k++) {
-        const int s = ax.tpe_bj_slot[k];
-        const TpeJC cp = tpe_jc(ds, ax.tpe_bj_pivot[k]), cg = tpe_jc(ds, ax.tpe_bj_gear[k]);
-        double vbx = T.V(s, 0), vby = T.V(s, 1), wb = T.V(s, 2);
-        {
-          double jx = (0.0 - (vbx - 0.0)) * cp.c0;
-          double jy = (0.0 - (vby - 0.0)) * cp.c0;
-          const double ox = T.BJ(k, 0), oy = T.BJ(k, 1);
-          d2 acc = dvclamp(D2(ox + jx, oy + jy), cp.c1);
-          T.BJ(k, 0) = acc.x; T.BJ(k, 1) = acc.y;
-          jx = acc.x - ox; jy = acc.y - oy;
-          vbx = vbx + jx * cp.mb; vby = vby + jy * cp.mb;
+      /* blocks: force-capped pivot + gear against the static body (entities.py:703-711).  Two blocks per
+       * trip with all loads issued first: the blocks are independent, and a lone warp per scheduler has
+       * nothing but instruction-level parallelism to hide shared-memory and fp64 latency with. */
+      for (int k = 0; k < nblk; k += 2) {
+        const bool two = k + 1 < nblk;
+        const int kb = two ? k + 1 : k;
+        const int sA = ax.tpe_bj_slot[k], sB = ax.tpe_bj_slot[kb];
+        const TpeJC cpA = tpe_jc(ds, ax.tpe_bj_pivot[k]), cgA = tpe_jc(ds, ax.tpe_bj_gear[k]);
+        const TpeJC cpB = tpe_jc(ds, ax.tpe_bj_pivot[kb]), cgB = tpe_jc(ds, ax.tpe_bj_gear[kb]);
+        double vxA = T.V(sA, 0), vyA = T.V(sA, 1), wA = T.V(sA, 2);
+        double vxB = T.V(sB, 0), vyB = T.V(sB, 1), wB = T.V(sB, 2);
+        const double oxA = T.BJ(k, 0), oyA = T.BJ(k, 1), biasA = T.BJ(k, 3);
+        const double oxB = T.BJ(kb, 0), oyB = T.BJ(kb, 1), biasB = T.BJ(kb, 3);
+        double gaA = T.BJ(k, 2), gaB = T.BJ(kb, 2);
+        double jxA = (0.0 - (vxA - 0.0)) * cpA.c0, jyA = (0.0 - (vyA - 0.0)) * cpA.c0;
+        double jxB = (0.0 - (vxB - 0.0)) * cpB.c0, jyB = (0.0 - (vyB - 0.0)) * cpB.c0;
+        const d2 accA = dvclamp(D2(oxA + jxA, oyA + jyA), cpA.c1);
+        const d2 accB = dvclamp(D2(oxB + jxB, oyB + jyB), cpB.c1);
+        jxA = accA.x - oxA; jyA = accA.y - oyA;
+        jxB = accB.x - oxB; jyB = accB.y - oyB;
+        vxA = vxA + jxA * cpA.mb; vyA = vyA + jyA * cpA.mb;
+        vxB = vxB + jxB * cpB.mb; vyB = vyB + jyB * cpB.mb;
+        double waA = 0.0, waB = 0.0;
+        tpe_gear(cgA, biasA, gaA, waA, wA);
+        tpe_gear(cgB, biasB, gaB, waB, wB);
+        T.BJ(k, 0) = accA.x; T.BJ(k, 1) = accA.y; T.BJ(k, 2) = gaA;
+        T.V(sA, 0) = vxA; T.V(sA, 1) = vyA; T.V(sA, 2) = wA;
+        if (two) {
+          T.BJ(kb, 0) = accB.x; T.BJ(kb, 1) = accB.y; T.BJ(kb, 2) = gaB;
+          T.V(sB, 0) = vxB; T.V(sB, 1) = vyB; T.V(sB, 2) = wB;
         }
-        {
-          double acc = T.BJ(k, 2), wa = 0.0;
-          tpe_gear(cg, T.BJ(k, 3), acc, wa, wb);
-          T.BJ(k, 2) = acc;
-        }
-        T.V(s, 0) = vbx; T.V(s, 1) = vby; T.V(s, 2) = wb;
       }
       /* the robot chain, in insertion order (entities.py:255-354) */
       rvx = T.V(s_robot, 0); rvy = T.V(s_robot, 1); rw = T.V(s_robot, 2);
