@@ -20,6 +20,7 @@ for r in rows[1:]:
     acc[name][1] += 1
 out = {k: v[0] / (v[1] / 2) for k, v in acc.items()}  # two metrics per launch
 out['_batch'] = 65536
+out['_env_id'] = 'ClusterColour-Demo-LoRes4E-v0'
 out['_source'] = sys.argv[2] if len(sys.argv) > 2 else sys.argv[1]
 json.dump(out, open('profiles/traffic.json', 'w'), indent=1)
 print(json.dumps(out, indent=1))
