@@ -608,27 +608,43 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     int n_items = 0;
     bool truncated = false;
     int res_p = 0, res_i = 0, res_k = 0;
-    for (int p = 0; p < nbp && !truncated; p++) {
+    /* pass 1 (all lanes in step): box test of every candidate pair -> bit mask in registers */
+    uint32_t pmask[(MG_MAX_BPAIRS + 31) / 32];
+#pragma unroll
+    for (int w = 0; w < (MG_MAX_BPAIRS + 31) / 32; w++) pmask[w] = 0u;
+    for (int p = 0; p < nbp; p++) {
       const int ga = sc.bpairs[p][0], gb = sc.bpairs[p][1];
-      if (!(T.gbb(ga, 0) <= T.gbb(gb, 2) && T.gbb(gb, 0) <= T.gbb(ga, 2) && T.gbb(ga, 1) <= T.gbb(gb, 3) &&
-            T.gbb(gb, 1) <= T.gbb(ga, 3)))
-        continue;
-      TPE_STAT(3);
-      const uint32_t ia_ = T.ginfo(ga), ib_ = T.ginfo(gb);
-      const float travelled = tpe_fadd_ru(T.path((int)(ia_ >> 16)), T.path((int)(ib_ >> 16)));
-      if (travelled < tpe_sep_get(T, p)) { TPE_STAT(4); continue; }
-      const int sa0 = (int)(ia_ & 0xFFu), na = (int)((ia_ >> 8) & 0xFFu);
-      const int sb0 = (int)(ib_ & 0xFFu), nbs = (int)((ib_ >> 8) & 0xFFu);
-      const int first_item = n_items;
-      for (int i = 0; i < na && !truncated; i++)
-        for (int k = 0; k < nbs; k++) {
-          if (n_items == T.L.nitems) { truncated = true; res_p = p; res_i = i; res_k = k; break; }
-          /* (the executing lane orders the two shapes by kind, as cpCollide does, in stage A) */
-          T.IT(n_items++) = (uint32_t)((sa0 + i) | ((sb0 + k) << 8) | (p << 16));
-          TPE_STAT(1);
-        }
-      /* LAST = settle the pair's separation after this item; CONT = the pair continues in the serial tail */
-      if (n_items > first_item) T.IT(n_items - 1) |= truncated ? TPE_IT_CONT : TPE_IT_LAST;
+      const bool hit = T.gbb(ga, 0) <= T.gbb(gb, 2) && T.gbb(gb, 0) <= T.gbb(ga, 2) && T.gbb(ga, 1) <= T.gbb(gb, 3) &&
+                       T.gbb(gb, 1) <= T.gbb(ga, 3);
+#pragma unroll
+      for (int w = 0; w < (MG_MAX_BPAIRS + 31) / 32; w++)
+        if ((p >> 5) == w) pmask[w] |= (hit ? 1u : 0u) << (p & 31);
+    }
+    /* pass 2 (lanes diverge, but only over their own few hits): separation cache, then the items */
+#pragma unroll
+    for (int w = 0; w < (MG_MAX_BPAIRS + 31) / 32; w++) {
+      uint32_t bits = pmask[w];
+      while (bits && !truncated) {
+        const int p = w * 32 + TPE_CTZ(bits);
+        bits &= bits - 1u;
+        TPE_STAT(3);
+        const int ga = sc.bpairs[p][0], gb = sc.bpairs[p][1];
+        const uint32_t ia_ = T.ginfo(ga), ib_ = T.ginfo(gb);
+        const float travelled = tpe_fadd_ru(T.path((int)(ia_ >> 16)), T.path((int)(ib_ >> 16)));
+        if (travelled < tpe_sep_get(T, p)) { TPE_STAT(4); continue; }
+        const int sa0 = (int)(ia_ & 0xFFu), na = (int)((ia_ >> 8) & 0xFFu);
+        const int sb0 = (int)(ib_ & 0xFFu), nbs = (int)((ib_ >> 8) & 0xFFu);
+        const int first_item = n_items;
+        for (int i = 0; i < na && !truncated; i++)
+          for (int k = 0; k < nbs; k++) {
+            if (n_items == T.L.nitems) { truncated = true; res_p = p; res_i = i; res_k = k; break; }
+            /* (the executing lane orders the two shapes by kind, as cpCollide does, in stage A) */
+            T.IT(n_items++) = (uint32_t)((sa0 + i) | ((sb0 + k) << 8) | (p << 16));
+            TPE_STAT(1);
+          }
+        /* LAST = settle the pair's separation after this item; CONT = the pair continues in the serial tail */
+        if (n_items > first_item) T.IT(n_items - 1) |= truncated ? TPE_IT_CONT : TPE_IT_LAST;
+      }
     }
 
     /* ---- narrowphase + contact cache lookup (cpCollide + cpArbiterUpdate).

@@ -656,7 +656,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_BLOCKS)
 k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, uint8_t* __restrict__ obs, int batch,
          int res_out, int ecap, int scap, int rcap, int only_fresh, int env0) {
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
-  constexpr int NV = (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESCHW4E) ? 1 : 2;
+  /* LoResStack and RAW keep their two views in separate planes, so the views are rendered one after the
+   * other through the same shared memory (NPASS = 2, one resident view): half the footprint, twice the CTAs
+   * per SM.  LoRes3EA interleaves both views in one pixel and keeps both resident. */
+  constexpr bool SEQ = (MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_RAW);
+  constexpr int NV = (MODE == MG_OBS_LORES3EA) ? 2 : 1;
+  constexpr int NPASS = SEQ ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_off[2 * MG_MAX_PRIMS + 2];
   __shared__ int s_misc[8];
@@ -684,13 +689,14 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       vsm[v].cover = reinterpret_cast<int32_t*>(p); p += sizeof(int32_t) * RGRID * RGRID;
     }
   }
+  const bool fresh = st.fresh != 0;
+  for (int pass = 0; pass < NPASS; pass++) {
   for (int v = 0; v < NV; v++) {
-    int view = (NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1);
+    int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
     build_view<SS>(vsm[v], st, sc, view, res_out, ecap, scap, s_off, s_misc);
     if (threadIdx.x == 0) s_misc[4] = 0; /* next tile to hand out */
     __syncthreads();
   }
-  const bool fresh = st.fresh != 0;
   const int T = res_out / RGRID;        /* output pixels per tile side (multiple of 4) */
   const int gpr = T / 4;                /* 4-pixel groups per tile row */
   const int gpt = gpr * T;              /* groups per tile */
@@ -743,8 +749,8 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       if ((MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_LORES3EA) &&
           !fresh) {
 #pragma unroll
-        for (int v = 0; v < ((MODE == MG_OBS_LORESSTACK) ? NV : 1); v++) {
-          size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)v * batch : 0;
+        for (int v = 0; v < 1; v++) {
+          size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * batch : 0;
           const uint4* ptr =
               reinterpret_cast<const uint4*>(obs + ((plane + env) * frame_px + (size_t)Y * res_out + X0) * 12);
           pre[v][0] = ptr[0]; pre[v][1] = ptr[1]; pre[v][2] = ptr[2];
@@ -764,8 +770,8 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       if (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK) {
         /* [B, R, R, 12] (LoResStack: [2, B, R, R, 12]): 4 pixels = 48 bytes = 3 x uint4 */
 #pragma unroll
-        for (int v = 0; v < NV; v++) {
-          size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)v * batch : 0;
+        for (int v = 0; v < 1; v++) {
+          size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * batch : 0;
           uint4* ptr = reinterpret_cast<uint4*>(obs + ((plane + env) * frame_px + (size_t)Y * res_out + X0) * 12);
           uint32_t w[12];
           if (!fresh) {
@@ -823,9 +829,9 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       } else {
         /* RAW [2, B, R, R, 3]: 4 pixels = 12 bytes = 3 x u32 */
 #pragma unroll
-        for (int v = 0; v < NV; v++) {
+        for (int v = 0; v < 1; v++) {
           uint32_t* ptr = reinterpret_cast<uint32_t*>(
-              obs + (((size_t)v * batch + env) * frame_px + (size_t)Y * res_out + X0) * 3);
+              obs + (((size_t)pass * batch + env) * frame_px + (size_t)Y * res_out + X0) * 3);
           uint32_t c0 = col[v][0], c1 = col[v][1], c2 = col[v][2], c3 = col[v][3];
           ptr[0] = c0 | (c1 << 24);
           ptr[1] = (c1 >> 8) | (c2 << 16);
@@ -834,12 +840,13 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       }
     }
   }
-  __syncthreads();
+  __syncthreads(); /* the next pass rebuilds the shared tables */
+  } /* pass */
   if (threadIdx.x == 0 && fresh) stg.fresh = 0;
 }
 
-static int n_views(int mode) {
-  return (mode == MG_OBS_LORES4E || mode == MG_OBS_LORES4A || mode == MG_OBS_LORESCHW4E) ? 1 : 2;
+static int n_views(int mode) { /* views resident in shared memory at a time */
+  return (mode == MG_OBS_LORES3EA) ? 2 : 1;
 }
 
 size_t mg_raster_smem_bytes(int mode, int ecap, int scap, int rcap) {
