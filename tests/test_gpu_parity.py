@@ -365,3 +365,65 @@ def test_mixed_task_batch_scores_match_oracle(built):
         assert int(st['overflow']) == 0
         assert np.array_equal(st['pos'][:nb], ost['pos'][:nb]), names[scene_ids[e]]
     venv.close()
+
+
+@pytest.mark.parametrize('task_name', TASKS)
+def test_full_episode_matches_committed_oracle_pins(built, task_name):
+    """CUDA path against the committed fixtures (tests/golden/oracle_pins.json):
+    a seeded full-episode rollout must end on the pinned poses, score and
+    frame checksums."""
+    import json
+    import os
+    import zlib
+    import torch
+    from magical_b200.vec_env import MagicalVecEnv
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, 'golden', 'oracle_pins.json')) as fh:
+        pin = json.load(fh)[task_name]
+    task = make_demo_task(task_name)
+    venv = MagicalVecEnv(task, 3, preproc='LoResStack', auto_reset=False)
+    venv.reset()
+    rng = np.random.RandomState(1234)
+    for _ in range(pin['steps']):
+        a = int(rng.randint(18)) if rng.rand() < 0.5 \
+            else int(rng.choice([1, 4, 7, 10, 13, 16]))
+        obs, rew, done, info = venv.step(
+            torch.from_numpy(np.full(3, a, dtype=np.int32)).cuda())
+    st = venv.get_state(1)
+    nb = int(st['n_bodies'])
+    assert bool(done[1].item()) == pin['done']
+    assert np.float32(info['eval_score'][1].item()) == np.float32(pin['score'])
+    assert np.allclose(st['pos'][:nb], pin['pos'], rtol=0, atol=1e-12)
+    assert np.allclose(st['angle'][:nb], pin['angle'], rtol=0, atol=1e-12)
+    obs = obs.cpu().numpy()
+    assert zlib.crc32(np.ascontiguousarray(obs[0, 1, :, :, 9:12]).tobytes()) == pin['allo_crc32']
+    assert zlib.crc32(np.ascontiguousarray(obs[1, 1, :, :, 9:12]).tobytes()) == pin['ego_crc32']
+    venv.close()
+
+
+def test_soak_contact_rich_batch_has_no_overflow(built):
+    """4096 ClusterColour environments driven into the block field for a whole
+    episode: no environment may hit a capacity limit (contacts, cache,
+    work items are all handled by spill / serial continuations)."""
+    import torch
+    import magical_b200 as magical
+    batch = 4096
+    venv = magical.make_vec('ClusterColour-Demo-LoRes4E-v0', batch,
+                            auto_reset=False)
+    venv.reset()
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(3)
+    push = torch.tensor([1, 4, 7, 10, 13, 16], dtype=torch.int32, device='cuda')
+    for t in range(240):
+        rnd = torch.randint(0, 18, (batch,), dtype=torch.int32, device='cuda',
+                            generator=gen)
+        pick = push[torch.randint(0, 6, (batch,), device='cuda', generator=gen)]
+        coin = torch.rand(batch, device='cuda', generator=gen) < 0.3
+        venv.step(torch.where(coin, rnd, pick))
+    most = 0
+    for e in range(0, batch, 16):
+        st = venv.get_state(e)
+        assert int(st['overflow']) == 0, e
+        most = max(most, int(st['n_contacts']))
+    assert most >= 4
+    venv.close()
