@@ -25,7 +25,8 @@
 cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
                               int lanes_per_env, int block_threads, cudaStream_t stream);
 cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int env0,
-                                  int count, const TpeLayout* L, double* spill, cudaStream_t stream);
+                                  int count, const TpeLayout* L, double* spill, uint32_t* scratch,
+                                  cudaStream_t stream);
 size_t mg_tpe_smem_bytes(const TpeLayout* L);
 size_t mg_tpe_spill_doubles_per_env(const TpeLayout* L);
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
@@ -57,6 +58,7 @@ struct mg_handle {
   int use_tpe;          /* K1 variant: 1 = thread per environment (mg_physics_tpe.h), 0 = lanes per environment */
   TpeLayout tpe;        /* private-word layout of the thread-per-environment kernel */
   double* d_spill;      /* its contact spill area */
+  uint32_t* d_scratch;  /* its per-environment work-item / separation-cache records (scratch_global layout) */
   /* mg_step software pipeline: the batch is cut into chunks whose physics and raster kernels run on two
    * internal streams, staggered so that the raster of chunk c overlaps the physics of chunk c + 1 (the
    * physics is latency-bound at ~13 % issue utilisation, the raster issue-bound: they share SMs well) */
@@ -220,15 +222,17 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
                               "(thread-per-environment kernel)%s", "");
   }
   if (h->use_tpe) {
-    int kcon = 5;
+    int kcon = 4;
     if (const char* ev = getenv("MG_TPE_KCON")) kcon = atoi(ev);
     if (kcon < 1) kcon = 1;
     if (kcon > TPE_MAX_CONTACTS) kcon = TPE_MAX_CONTACTS;
     int nitems = 48;
     if (const char* ev = getenv("MG_TPE_NITEMS")) nitems = atoi(ev);
-    h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, max_pairs, kcon, nitems);
+    int scratch_global = 1;
+    if (const char* ev = getenv("MG_TPE_SCRATCH")) scratch_global = strcmp(ev, "smem") != 0;
+    h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, max_pairs, kcon, nitems, scratch_global);
     while (mg_tpe_smem_bytes(&h->tpe) > 200 * 1024 && kcon > 1)
-      h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, max_pairs, --kcon, nitems);
+      h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, max_pairs, --kcon, nitems, scratch_global);
   }
   cudaError_t e;
   if ((e = cudaMalloc(&h->d_states, sizeof(EnvState) * (size_t)cfg->batch)) != cudaSuccess ||
@@ -237,6 +241,9 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
       (e = cudaMalloc(&h->d_scene_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
       (h->use_tpe && mg_tpe_spill_doubles_per_env(&h->tpe) > 0 &&
        (e = cudaMalloc(&h->d_spill, sizeof(double) * mg_tpe_spill_doubles_per_env(&h->tpe) * (size_t)cfg->batch)) !=
+           cudaSuccess) ||
+      (h->use_tpe && h->tpe.scratch_global &&
+       (e = cudaMalloc(&h->d_scratch, sizeof(uint32_t) * (size_t)h->tpe.scratch_u32 * ((size_t)cfg->batch + 32))) !=
            cudaSuccess)) {
     mg_destroy(h);
     return fail(MG_E_NOMEM, "mg_create: cudaMalloc: %s", cudaGetErrorString(e));
@@ -295,6 +302,7 @@ int mg_destroy(mg_handle* h) {
   cudaFree(h->d_ids);
   cudaFree(h->d_scene_ids);
   cudaFree(h->d_spill);
+  cudaFree(h->d_scratch);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   for (int i = 0; i < 2; i++) {
     if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
@@ -354,7 +362,7 @@ static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_de
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   if (h->use_tpe)
     CUDA_TRY(mg_launch_physics_tpe(h->d_states, h->d_scenes, actions_dev, 0, h->cfg.batch, &h->tpe, h->d_spill,
-                                   h->stream));
+                                   h->d_scratch, h->stream));
   else
     CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads,
                                h->stream));
@@ -382,7 +390,8 @@ static int step_pipelined(mg_handle* h, const int32_t* actions_dev, float* rewar
     cudaStream_t st = h->side[c & 1];
     /* stagger: the physics of chunk c starts when the physics of chunk c - 1 has finished */
     if (c > 0) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_phys[(c - 1) & 1], 0));
-    CUDA_TRY(mg_launch_physics_tpe(h->d_states, h->d_scenes, actions_dev, env0, count, &h->tpe, h->d_spill, st));
+    CUDA_TRY(mg_launch_physics_tpe(h->d_states, h->d_scenes, actions_dev, env0, count, &h->tpe, h->d_spill, h->d_scratch,
+                                   st));
     CUDA_TRY(cudaEventRecord(h->ev_phys[c & 1], st));
     CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, env0, count, h->cfg.auto_reset, 0, h->cfg.n_scenes,
                               (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, st));

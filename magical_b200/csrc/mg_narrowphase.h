@@ -103,6 +103,7 @@ MG_HD void sv_bb(const ShapeView& s, double bb[4]) {
     bb[0] = l - s.radius; bb[1] = b - s.radius; bb[2] = r + s.radius; bb[3] = t + s.radius;
   } else {
     double l = MG_INF, r = -MG_INF, b = MG_INF, t = -MG_INF;
+#pragma unroll 1
     for (int i = 0; i < s.nvert; i++) {
       d2 v = sv_vert(s, i);
       l = dminf(l, v.x); r = dmaxf(r, v.x); b = dminf(b, v.y); t = dmaxf(t, v.y);
@@ -119,6 +120,7 @@ MG_HD int sv_support_index(const ShapeView& s, d2 n) {
   if (s.kind == 1) return (ddot(sv_vert(s, 0), n) > ddot(sv_vert(s, 1), n)) ? 0 : 1;
   double best = -MG_INF;
   int index = 0;
+#pragma unroll 1
   for (int i = 0; i < s.nvert; i++) {
     double d = ddot(sv_vert(s, i), n);
     if (d > best) { best = d; index = i; }
@@ -178,28 +180,67 @@ MG_HD ClosestPts closest_points_new(const ShapeView& s1, const ShapeView& s2, Mi
   return pts;
 }
 
-/* EPA as a loop over ping-pong hull buffers. */
-MG_HD_NOINLINE ClosestPts mg_epa(const ShapeView& s1, const ShapeView& s2, MinkPoint v0, MinkPoint v1, MinkPoint v2) {
-  MinkPoint bufA[MG_EPA_HULL_CAP], bufB[MG_EPA_HULL_CAP];
+/* GJK closest points with the EPA penetration search folded into the same loop.  The loop is a small state
+ * machine (0, 1: the two initial supports; 2: a GJK step; 3: an EPA step) so that the support mapping --
+ * the bulk of the code and of the run time -- exists ONCE: lanes that are in different stages of different
+ * shape pairs stay converged through it, and the instruction footprint stays small (the kernels that
+ * inline this are instruction-fetch sensitive).  Every step performs exactly the arithmetic of Chipmunk's
+ * recursive GJKRecurse / EPARecurse, in the same order. */
+MG_HD_NOINLINE ClosestPts mg_gjk(const ShapeView& s1, const ShapeView& s2, const double* bb1, const double* bb2) {
+  d2 c1 = dlerp(D2(bb1[0], bb1[1]), D2(bb1[2], bb1[3]), 0.5);
+  d2 c2 = dlerp(D2(bb2[0], bb2[1]), D2(bb2[2], bb2[3]), 0.5);
+  const d2 axis = dperp(dsub(c1, c2));
+  MinkPoint v0, v1;             /* GJK simplex */
+  MinkPoint bufA[MG_EPA_HULL_CAP], bufB[MG_EPA_HULL_CAP]; /* EPA hull, ping-pong */
   MinkPoint* hull = bufA;
   MinkPoint* hull2 = bufB;
-  hull[0] = v0; hull[1] = v1; hull[2] = v2;
-  int count = 3;
-  for (int iteration = 1;; iteration++) {
-    int mini = 0;
-    double min_dist = MG_INF;
-    for (int j = 0, i = count - 1; j < count; i = j, j++) {
-      double d = closest_dist(hull[i].ab, hull[j].ab);
-      if (d < min_dist) { min_dist = d; mini = i; }
+  int count = 0, mini = 0;
+  MinkPoint e0, e1;             /* closest EPA edge / the pair handed to closest_points_new */
+  v0.ab = v1.ab = e0.ab = e1.ab = D2(0, 0);
+  v0.id = v1.id = e0.id = e1.id = 0u;
+  int phase = 0, iteration = 1, eiter = 1;
+  d2 dir = axis;
+  for (;;) {
+    if (phase == 2) {
+      if (iteration > MG_MAX_GJK_ITERATIONS) { e0 = v0; e1 = v1; break; }
+      if (check_point_greater(v1.ab, v0.ab, D2(0, 0))) { MinkPoint t = v0; v0 = v1; v1 = t; }
+      double t = closest_t(v0.ab, v1.ab);
+      dir = (-1.0 < t && t < 1.0) ? dperp(dsub(v1.ab, v0.ab)) : dneg(lerp_t(v0.ab, v1.ab, t));
+    } else if (phase == 3) {
+      mini = 0;
+      double min_dist = MG_INF;
+#pragma unroll 1
+      for (int j = 0, i = count - 1; j < count; i = j, j++) {
+        double d = closest_dist(hull[i].ab, hull[j].ab);
+        if (d < min_dist) { min_dist = d; mini = i; }
+      }
+      e0 = hull[mini];
+      e1 = hull[(mini + 1) % count];
+      dir = dperp(dsub(e1.ab, e0.ab));
     }
-    MinkPoint e0 = hull[mini];
-    MinkPoint e1 = hull[(mini + 1) % count];
-    MinkPoint p = mk_support(s1, s2, dperp(dsub(e1.ab, e0.ab)));
-    bool duplicate = (p.id == e0.id || p.id == e1.id);
-    if (!duplicate && check_point_greater(e0.ab, e1.ab, p.ab) && iteration < MG_MAX_EPA_ITERATIONS &&
+    const MinkPoint p = mk_support(s1, s2, dir); /* the one support-mapping site */
+    if (phase == 0) { v0 = p; dir = dneg(axis); phase = 1; continue; }
+    if (phase == 1) { v1 = p; phase = 2; continue; }
+    if (phase == 2) {
+      if (check_point_greater(p.ab, v0.ab, D2(0, 0)) && check_point_greater(v1.ab, p.ab, D2(0, 0))) {
+        /* the origin is inside the simplex: the shapes overlap, continue with EPA on (v0, p, v1) */
+        hull[0] = v0; hull[1] = p; hull[2] = v1;
+        count = 3;
+        phase = 3;
+        continue;
+      }
+      if (check_axis(v0.ab, v1.ab, p.ab, dir)) { e0 = v0; e1 = v1; break; }
+      if (closest_dist(v0.ab, p.ab) < closest_dist(p.ab, v1.ab)) v1 = p; else v0 = p;
+      iteration++;
+      continue;
+    }
+    /* phase 3: grow the hull by p, or stop at the closest edge */
+    const bool duplicate = (p.id == e0.id || p.id == e1.id);
+    if (!duplicate && check_point_greater(e0.ab, e1.ab, p.ab) && eiter < MG_MAX_EPA_ITERATIONS &&
         count + 1 < MG_EPA_HULL_CAP) {
       int count2 = 1;
       hull2[0] = p;
+#pragma unroll 1
       for (int i = 0; i < count; i++) {
         int index = (mini + 1 + i) % count;
         d2 h0 = hull2[count2 - 1].ab;
@@ -209,30 +250,12 @@ MG_HD_NOINLINE ClosestPts mg_epa(const ShapeView& s1, const ShapeView& s2, MinkP
       }
       MinkPoint* tmp = hull; hull = hull2; hull2 = tmp;
       count = count2;
+      eiter++;
     } else {
-      return closest_points_new(s1, s2, e0, e1);
+      break; /* (e0, e1) is the closest edge */
     }
   }
-}
-
-MG_HD_NOINLINE ClosestPts mg_gjk(const ShapeView& s1, const ShapeView& s2, const double* bb1, const double* bb2) {
-  d2 c1 = dlerp(D2(bb1[0], bb1[1]), D2(bb1[2], bb1[3]), 0.5);
-  d2 c2 = dlerp(D2(bb2[0], bb2[1]), D2(bb2[2], bb2[3]), 0.5);
-  d2 axis = dperp(dsub(c1, c2));
-  MinkPoint v0 = mk_support(s1, s2, axis);
-  MinkPoint v1 = mk_support(s1, s2, dneg(axis));
-  for (int iteration = 1;;) {
-    if (iteration > MG_MAX_GJK_ITERATIONS) return closest_points_new(s1, s2, v0, v1);
-    if (check_point_greater(v1.ab, v0.ab, D2(0, 0))) { MinkPoint t = v0; v0 = v1; v1 = t; }
-    double t = closest_t(v0.ab, v1.ab);
-    d2 n = (-1.0 < t && t < 1.0) ? dperp(dsub(v1.ab, v0.ab)) : dneg(lerp_t(v0.ab, v1.ab, t));
-    MinkPoint p = mk_support(s1, s2, n);
-    if (check_point_greater(p.ab, v0.ab, D2(0, 0)) && check_point_greater(v1.ab, p.ab, D2(0, 0)))
-      return mg_epa(s1, s2, v0, p, v1);
-    if (check_axis(v0.ab, v1.ab, p.ab, n)) return closest_points_new(s1, s2, v0, v1);
-    if (closest_dist(v0.ab, p.ab) < closest_dist(p.ab, v1.ab)) v1 = p; else v0 = p;
-    iteration++;
-  }
+  return closest_points_new(s1, s2, e0, e1);
 }
 
 struct SupEdge {

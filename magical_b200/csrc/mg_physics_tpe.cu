@@ -14,7 +14,7 @@
 
 __global__ void __launch_bounds__(TPE_THREADS)
 k_physics_tpe(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, const int32_t* __restrict__ actions,
-              int env0, int count, TpeLayout L, double* __restrict__ spill) {
+              int env0, int count, TpeLayout L, double* __restrict__ spill, uint32_t* __restrict__ scratch) {
   extern __shared__ __align__(16) double tpe_words[];
   int env = env0 + blockIdx.x * TPE_THREADS + threadIdx.x;
   const int batch = env0 + count; /* this launch covers environments [env0, env0 + count) */
@@ -32,6 +32,8 @@ k_physics_tpe(EnvState* __restrict__ states, const DeviceScene* __restrict__ sce
   T.spill = spill ? spill + (size_t)env * (size_t)((TPE_MAX_CONTACTS - L.kcon) * TPE_CON_WORDS) : nullptr;
   T.slotmap = 0;
   T.static_slot = 0;
+  /* scratch records are indexed by launch slot (not by the clamped env), so every lane has its own */
+  T.bind_scratch(scratch ? scratch + (size_t)(env0 + blockIdx.x * TPE_THREADS + threadIdx.x) * (size_t)L.scratch_u32 : nullptr);
   tpe_env_step<TPE_THREADS>(T, G, ds, actions[env], live);
 }
 
@@ -39,7 +41,8 @@ size_t mg_tpe_smem_bytes(const TpeLayout* L) { return (size_t)L->words * sizeof(
 size_t mg_tpe_spill_doubles_per_env(const TpeLayout* L) { return (size_t)(TPE_MAX_CONTACTS - L->kcon) * TPE_CON_WORDS; }
 
 cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int env0,
-                                  int count, const TpeLayout* L, double* spill, cudaStream_t stream) {
+                                  int count, const TpeLayout* L, double* spill, uint32_t* scratch,
+                                  cudaStream_t stream) {
   const size_t smem = mg_tpe_smem_bytes(L);
   static size_t configured = 0;
   if (configured < smem) {
@@ -50,6 +53,6 @@ cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, c
     configured = smem;
   }
   k_physics_tpe<<<(count + TPE_THREADS - 1) / TPE_THREADS, TPE_THREADS, smem, stream>>>(states, scenes, actions, env0,
-                                                                                      count, *L, spill);
+                                                                                      count, *L, spill, scratch);
   return cudaGetLastError();
 }

@@ -97,17 +97,21 @@ struct TpeLayout {
   int kcon;     /* contacts that fit in the private words */
   int off_it, nitems; /* narrowphase work items of the sub-step (32 bits each) */
   int off_sep;        /* separation cache: one 16-bit truncated float per candidate group pair */
+  int scratch_global; /* 1: items + separation cache live in a per-environment scratch record in HBM/L2
+                         (touched a few times per sub-step) instead of the private words */
+  int scratch_u32;    /* 32-bit words of one environment's scratch record */
   int words;    /* 8-byte words per environment */
 };
 
-static inline TpeLayout tpe_make_layout(int nslots, int nblocks, int ncgroups, int nbpairs, int kcon, int nitems) {
+static inline TpeLayout tpe_make_layout(int nslots, int nblocks, int ncgroups, int nbpairs, int kcon, int nitems,
+                                        int scratch_global) {
   TpeLayout L;
   L.nslots = nslots;
   L.nblocks = nblocks;
   L.off_bv = nslots * 3;
   L.off_pr = L.off_bv + nslots * 3;
   L.off_bj = L.off_pr + (nslots - 1) * 5;
-  L.off_path = L.off_bj + nblocks * 4;
+  L.off_path = L.off_bj + nblocks * 3;
   L.off_con = L.off_path + (nslots + 1) / 2;
   int con_words = kcon * TPE_CON_WORDS;
   if (con_words < ncgroups * 3) con_words = ncgroups * 3; /* group boxes + info share the contact words */
@@ -117,6 +121,9 @@ static inline TpeLayout tpe_make_layout(int nslots, int nblocks, int ncgroups, i
   L.nitems = nitems < 2 ? 2 : (nitems > 64 ? 64 : (nitems + 1) / 2 * 2); /* item indices are 6 bits */
   L.off_sep = L.off_it + L.nitems / 2;
   L.words = L.off_sep + (nbpairs + 3) / 4;
+  L.scratch_global = scratch_global;
+  L.scratch_u32 = (L.nitems + (nbpairs + 1) / 2 + 3) / 4 * 4;
+  if (scratch_global) L.words = L.off_it;
   return L;
 }
 
@@ -126,6 +133,9 @@ struct Tpe {
   double* wd;   /* the three views of the private words, each already offset by the lane */
   float* wf;
   uint16_t* wh;
+  uint32_t* itp;  /* work items: item k at itp[k * it_st]; the next lane's array starts it_lane elements on */
+  uint16_t* sepp; /* separation cache, same stride */
+  int it_st, it_lane;
   TpeLayout L;
   double* spill; /* [TPE_MAX_CONTACTS - kcon][TPE_CON_WORDS] contiguous, or null */
   uint64_t slotmap;
@@ -133,13 +143,23 @@ struct Tpe {
   MG_HDM double& V(int s, int k) const { return wd[(s * 3 + k) * S]; }
   MG_HDM double& Bv(int s, int k) const { return wd[(L.off_bv + s * 3 + k) * S]; }
   MG_HDM double& PR(int s, int k) const { return wd[(L.off_pr + s * 5 + k) * S]; } /* x y angle cos sin */
-  MG_HDM double& BJ(int b, int k) const { return wd[(L.off_bj + b * 4 + k) * S]; } /* pivot x,y  gear  gear bias */
+  MG_HDM double& BJ(int b, int k) const { return wd[(L.off_bj + b * 3 + k) * S]; } /* pivot x,y  gear */
   MG_HDM float& path(int s) const { return wf[(L.off_path * 2 + s) * S]; }
   /* group box l, b, r, t (k = 0..3) and, at k = 4, shape0 | nshape << 8 | slot << 16 of the group */
   MG_HDM float& gbb(int g, int k) const { return wf[(L.off_con * 2 + g * 6 + k) * S]; }
   MG_HDM uint32_t& ginfo(int g) const { return reinterpret_cast<uint32_t*>(wf)[(L.off_con * 2 + g * 6 + 4) * S]; }
-  MG_HDM uint32_t& IT(int k) const { return reinterpret_cast<uint32_t*>(wf)[(L.off_it * 2 + k) * S]; }
-  MG_HDM uint16_t& SEP(int p) const { return wh[(L.off_sep * 4 + p) * S]; }
+  MG_HDM uint32_t& IT(int k) const { return itp[k * it_st]; }
+  MG_HDM uint16_t& SEP(int p) const { return sepp[p * it_st]; }
+  /* bind the item / separation-cache views: private words, or `scratch` = this lane's record in HBM */
+  MG_HDM void bind_scratch(uint32_t* scratch) {
+    if (L.scratch_global) {
+      itp = scratch; sepp = reinterpret_cast<uint16_t*>(scratch + L.nitems); it_st = 1; it_lane = L.scratch_u32;
+    } else {
+      itp = reinterpret_cast<uint32_t*>(wf) + (size_t)L.off_it * 2 * S;
+      sepp = wh + (size_t)L.off_sep * 4 * S;
+      it_st = S; it_lane = 1;
+    }
+  }
   MG_HDM int slot(int body) const { /* body index or <0 / MG_MAX_BODIES for the static body */
     return (body < 0 || body >= MG_MAX_BODIES) ? static_slot : (int)((slotmap >> (4 * body)) & 15u);
   }
@@ -497,7 +517,6 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     const double2 ap = G->jacc[ax.tpe_bj_pivot[k]];
     T.BJ(k, 0) = ap.x; T.BJ(k, 1) = ap.y;
     T.BJ(k, 2) = G->jacc[ax.tpe_bj_gear[k]].x;
-    T.BJ(k, 3) = 0.0;
   }
   for (int p = 0; p < nbp; p++) T.SEP(p) = 0;
   /* control body (kinematic) and the two eye bodies (no shapes) */
@@ -710,6 +729,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
           const int oexcl = tpe_shfl<S>(excl, owner);
           Tpe<S> To = T;
           To.wd = T.wd - lane + owner; To.wf = T.wf - lane + owner; To.wh = T.wh - lane + owner;
+          To.itp = T.itp + (owner - lane) * T.it_lane;
           To.slotmap = tpe_shfl64<S>(T.slotmap, owner);
           To.static_slot = tpe_shfl<S>(T.static_slot, owner);
           const DeviceScene* dso = (const DeviceScene*)tpe_shfl64<S>((uint64_t)ds, owner);
@@ -750,6 +770,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
           const uint64_t osurv = tpe_shfl64<S>(surv, owner);
           Tpe<S> To = T;
           To.wd = T.wd - lane + owner; To.wf = T.wf - lane + owner; To.wh = T.wh - lane + owner;
+          To.itp = T.itp + (owner - lane) * T.it_lane;
           To.slotmap = tpe_shfl64<S>(T.slotmap, owner);
           To.static_slot = tpe_shfl<S>(T.static_slot, owner);
           const DeviceScene* dso = (const DeviceScene*)tpe_shfl64<S>((uint64_t)ds, owner);
@@ -907,14 +928,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
   } while (0)
     TPE_LIMIT_PRESTEP(b_lim0, a_lim0, jr0 + 5, s_f0);
     TPE_LIMIT_PRESTEP(b_lim1, a_lim1, jr0 + 8, s_f1);
-    /* blocks' gear bias (drag joints against the static body) */
-    for (int k = 0; k < nblk; k++) {
-      const int jg = ax.tpe_bj_gear[k];
-      const mg_joint_t& J = sc.joints[jg];
-      const double maxBias = J.max_bias;
-      const double ang_b = T.PR(ax.tpe_bj_slot[k], 2);
-      T.BJ(k, 3) = dclamp(-ax.j_bcoef[jg] * (ang_b * J.p1 - 0.0 - J.p0) / dt, -maxBias, maxBias);
-    }
+    /* (the blocks' drag gears have max_bias = 0, checked by mg_build_tpe_aux: their bias is exactly +0.0) */
 
     /* chain velocities live in registers while joints run */
     double rvx = T.V(s_robot, 0), rvy = T.V(s_robot, 1), rw = T.V(s_robot, 2);
@@ -1057,8 +1071,8 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
         const TpeJC cpB = tpe_jc(ds, ax.tpe_bj_pivot[kb]), cgB = tpe_jc(ds, ax.tpe_bj_gear[kb]);
         double vxA = T.V(sA, 0), vyA = T.V(sA, 1), wA = T.V(sA, 2);
         double vxB = T.V(sB, 0), vyB = T.V(sB, 1), wB = T.V(sB, 2);
-        const double oxA = T.BJ(k, 0), oyA = T.BJ(k, 1), biasA = T.BJ(k, 3);
-        const double oxB = T.BJ(kb, 0), oyB = T.BJ(kb, 1), biasB = T.BJ(kb, 3);
+        const double oxA = T.BJ(k, 0), oyA = T.BJ(k, 1), biasA = 0.0;
+        const double oxB = T.BJ(kb, 0), oyB = T.BJ(kb, 1), biasB = 0.0;
         double gaA = T.BJ(k, 2), gaB = T.BJ(kb, 2);
         double jxA = (0.0 - (vxA - 0.0)) * cpA.c0, jyA = (0.0 - (vyA - 0.0)) * cpA.c0;
         double jxB = (0.0 - (vxB - 0.0)) * cpB.c0, jyB = (0.0 - (vyB - 0.0)) * cpB.c0;

@@ -117,6 +117,7 @@ static inline void mg_build_tpe_aux(const mg_scene_t* s, mg_scene_aux_t* aux) {
     if (p->b < 0 || p->b >= s->n_bodies || !shaped[p->b] || used_body[p->b] || nblk >= MG_MAX_BLOCKS) return;
     if (p->b == robot || p->b == s->finger_body[0] || p->b == s->finger_body[1]) return;
     if (s->bodies[p->b].kind != MG_BODY_DYNAMIC || g->p1 == 0.0) return;
+    if (g->max_bias != 0.0) return; /* entities.py:709: pure angular drag, its bias is exactly zero */
     used_body[p->b] = 1;
     aux->tpe_bj_pivot[nblk] = (uint8_t)j;
     aux->tpe_bj_gear[nblk] = (uint8_t)(j + 1);

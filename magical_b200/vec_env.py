@@ -41,7 +41,8 @@ class MagicalVecEnv:
     """
 
     def __init__(self, task, batch, preproc=None, device=0, auto_reset=True,
-                 n_scenes=1, seed=None, scenes=None, stream=None):
+                 n_scenes=1, seed=None, scenes=None, stream=None,
+                 alloc_obs=True):
         import torch
         if not torch.cuda.is_available():
             raise _native.NativeError(
@@ -79,16 +80,20 @@ class MagicalVecEnv:
                 cfg.ctypes.data, self.scenes.ctypes.data,
                 ctypes.c_void_p(self._stream.cuda_stream),
                 ctypes.byref(self._h)))
+            # alloc_obs=False: physics-only use (step_physics / eval_score);
+            # step() and render() then fail with "no observation buffer bound"
             self.obs = torch.zeros(obs_shape(self.mode, self.batch, res),
-                                   dtype=torch.uint8, device=self.device)
+                                   dtype=torch.uint8, device=self.device) \
+                if alloc_obs else None
             self.reward = torch.zeros(self.batch, dtype=torch.float32,
                                       device=self.device)
             self.done = torch.zeros(self.batch, dtype=torch.uint8,
                                     device=self.device)
             self.score = torch.zeros(self.batch, dtype=torch.float32,
                                      device=self.device)
-        _native.check(self._lib.mg_bind_obs(self._h, self.obs.data_ptr(),
-                                            self.obs.numel()))
+        if self.obs is not None:
+            _native.check(self._lib.mg_bind_obs(self._h, self.obs.data_ptr(),
+                                                self.obs.numel()))
 
     # -- gym-like batched API ---------------------------------------------
     def reset(self, env_ids=None, scene_ids=None):

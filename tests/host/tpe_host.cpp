@@ -14,6 +14,7 @@ struct TpeHostEnv {
   TpeLayout L;
   std::vector<double> words;
   std::vector<double> spill;
+  std::vector<uint32_t> scratch;
   int use_spill;
 };
 
@@ -37,11 +38,12 @@ static void host_reset(TpeHostEnv* e) {
 
 extern "C" {
 
-TpeHostEnv* tpeh_create(const mg_scene_t* scene, int kcon, int use_spill, int nitems) {
+TpeHostEnv* tpeh_create(const mg_scene_t* scene, int kcon, int use_spill, int nitems, int scratch_global) {
   TpeHostEnv* e = new TpeHostEnv();
   e->ds.s = *scene;
   if (mg_build_scene_aux(scene, &e->ds.aux) || !e->ds.aux.tpe_ok) { delete e; return nullptr; }
-  e->L = tpe_make_layout(e->ds.aux.tpe_nslots, e->ds.aux.tpe_nblocks, scene->n_cgroups, scene->n_bpairs, kcon, nitems);
+  e->L = tpe_make_layout(e->ds.aux.tpe_nslots, e->ds.aux.tpe_nblocks, scene->n_cgroups, scene->n_bpairs, kcon, nitems, scratch_global);
+  e->scratch.assign((size_t)e->L.scratch_u32, 0u);
   e->words.assign((size_t)e->L.words, 0.0);
   e->spill.assign((size_t)TPE_MAX_CONTACTS * TPE_CON_WORDS, 0.0);
   e->use_spill = use_spill;
@@ -62,6 +64,7 @@ void tpeh_step(TpeHostEnv* e, int action) {
   T.spill = e->use_spill ? e->spill.data() : nullptr;
   T.slotmap = 0;
   T.static_slot = 0;
+  T.bind_scratch(e->scratch.data());
   tpe_env_step<1>(T, &e->st, &e->ds, action, true);
   e->st.episode_steps++;
 }

@@ -33,9 +33,10 @@ def _compare(st, ost, tag):
     return nc
 
 
-def _rollout(rec, actions, kcon=8, spill=True, nitems=32, max_surv=None):
+def _rollout(rec, actions, kcon=8, spill=True, nitems=32, max_surv=None,
+             scratch_global=True):
     env = TpeHostEnv(rec, kcon=kcon, spill=spill, nitems=nitems,
-                     max_surv=max_surv)
+                     max_surv=max_surv, scratch_global=scratch_global)
     orc = OracleEnv(rec, det_sincos=True)
     most = 0
     for t, a in enumerate(actions):
@@ -95,6 +96,16 @@ def test_item_word_overflow_takes_the_serial_tail(nitems):
                 for _ in range(200)]
         most = _rollout(rec, acts, nitems=nitems)
         assert most >= 2
+
+
+def test_items_and_sep_cache_in_private_words_layout():
+    """The alternative layout (work items + separation cache in the private
+    words instead of the per-environment scratch record) gives the same bits."""
+    rec = make_demo_task('ClusterColour').build_scene()
+    rng = np.random.RandomState(6)
+    acts = [int(rng.randint(18)) if rng.rand() < 0.5
+            else int(rng.choice([1, 4, 7, 10, 13, 16])) for _ in range(120)]
+    _rollout(rec, acts, scratch_global=False)
 
 
 def test_survivor_list_overflow_continues_serially():

@@ -39,7 +39,7 @@ def lib(max_surv=None):
         L = ctypes.CDLL(LIB)
         vp, i32, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
         L.tpeh_create.restype = vp
-        L.tpeh_create.argtypes = [vp, i32, i32, i32]
+        L.tpeh_create.argtypes = [vp, i32, i32, i32, i32]
         L.tpeh_destroy.argtypes = [vp]
         L.tpeh_reset.argtypes = [vp]
         L.tpeh_step.argtypes = [vp, i32]
@@ -53,11 +53,12 @@ def lib(max_surv=None):
 
 class TpeHostEnv:
     def __init__(self, scene_record, kcon=8, spill=True, nitems=32,
-                 max_surv=None):
+                 max_surv=None, scratch_global=True):
         self._lib = lib(max_surv)
         self._scene = np.ascontiguousarray(scene_record).copy()
         self._h = self._lib.tpeh_create(self._scene.ctypes.data, kcon,
-                                        int(spill), nitems)
+                                        int(spill), nitems,
+                                        int(scratch_global))
         assert self._h, 'scene rejected by the thread-per-env path'
 
     @property
