@@ -631,13 +631,20 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     uint32_t pmask[(MG_MAX_BPAIRS + 31) / 32];
 #pragma unroll
     for (int w = 0; w < (MG_MAX_BPAIRS + 31) / 32; w++) pmask[w] = 0u;
-    for (int p = 0; p < nbp; p++) {
-      const int ga = sc.bpairs[p][0], gb = sc.bpairs[p][1];
-      const bool hit = T.gbb(ga, 0) <= T.gbb(gb, 2) && T.gbb(gb, 0) <= T.gbb(ga, 2) && T.gbb(ga, 1) <= T.gbb(gb, 3) &&
-                       T.gbb(gb, 1) <= T.gbb(ga, 3);
+    for (int w0 = 0; w0 * 32 < nbp; w0++) {
+      uint32_t m = 0u;
+      const int pe = (nbp - w0 * 32 < 32) ? nbp - w0 * 32 : 32;
+      for (int b = 0; b < pe; b++) {
+        const int p = w0 * 32 + b;
+        const unsigned pr = TPE_LDG(reinterpret_cast<const unsigned short*>(&sc.bpairs[p][0]));
+        const int ga = (int)(pr & 0xFFu), gb = (int)(pr >> 8);
+        const bool hit = T.gbb(ga, 0) <= T.gbb(gb, 2) && T.gbb(gb, 0) <= T.gbb(ga, 2) &&
+                         T.gbb(ga, 1) <= T.gbb(gb, 3) && T.gbb(gb, 1) <= T.gbb(ga, 3);
+        m |= (hit ? 1u : 0u) << b;
+      }
 #pragma unroll
       for (int w = 0; w < (MG_MAX_BPAIRS + 31) / 32; w++)
-        if ((p >> 5) == w) pmask[w] |= (hit ? 1u : 0u) << (p & 31);
+        if (w0 == w) pmask[w] = m;
     }
     /* pass 2 (lanes diverge, but only over their own few hits): separation cache, then the items */
 #pragma unroll
