@@ -200,7 +200,8 @@ def run_b200(args, env_id, batch):
     dev = torch.device('cuda', local_rank)
     K, W = args.steps, args.warmup
 
-    venv = magical.make_vec(env_id, batch, device=local_rank, auto_reset=True)
+    # fixed seed: the randomised variants sample their scene pool from it (reproducible workload)
+    venv = magical.make_vec(env_id, batch, device=local_rank, auto_reset=True, seed=1234 + rank)
     venv.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(42 + rank)

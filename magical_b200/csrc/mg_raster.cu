@@ -156,68 +156,44 @@ __device__ __forceinline__ int last_true(float est, int cmin, int cmax, F ok) {
   return i;
 }
 
-/* exact covered interval of sample row j for primitive R (empty => lo > hi) */
+/* exact covered interval of sample row j for a thick line segment R (empty => lo > hi); polygons get
+ * their spans from the (edge, row) items of build_view */
 __device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restrict__ edges,
                                           const float4* __restrict__ eaux, int j) {
+  (void)eaux;
   int lo = R.col0, hi = R.col1;
   const float y = (float)j + 0.5f;
-  if (R.ne > 0) {
-    const int e1 = R.e0 + R.ne;
-    /* An edge can only bound this row if the row lies within one sample of the edge's own y-extent:
-     * the polygon is convex, so edges further away are satisfied with a margin (>= 0.05 px for the
-     * 100-gons, more for everything else) that is far above fp32 rounding.  Rows beyond the
-     * polygon's vertices are empty. */
-    if (y > R.ymax + 0.01f || y < R.ymin - 0.01f) return make_short2((short)lo, (short)(lo - 1));
-    for (int e = R.e0; e < e1 && lo <= hi; e++) {
-      const float4 X = eaux[e];
-      /* only edges whose own y-extent comes within one sample of this row can bound it */
-      if (y < X.z - 1.0f || y > X.w + 1.0f) continue;
-      const float4 E = edges[e];
-      const float A = E.x;
-      const float t = fmaf(E.y, y, E.z);
-      auto ok = [&](int i) { return fmaf(A, (float)i + 0.5f, t) >= 0.0f; };
-      const float est = fmaf(X.x, y, X.y) - 0.5f; /* boundary column estimate, corrected exactly below */
-      if (A > 0.0f) {
-        lo = first_true(est, lo, hi, ok);
-      } else if (A < 0.0f) {
-        hi = last_true(est, lo, hi, ok);
-      } else if (!(t >= 0.0f)) {
-        hi = lo - 1;
-      }
-    }
+  /* thick line segment: !(along < 0 || along > L || |perp| > hw), each bound monotone in x */
+  float4 p = edges[R.e0], q = edges[R.e0 + 1];
+  const float ry = y - p.y;
+  const float ca = ry * p.w;      /* along = fmaf(rx, ux, ry*uy) */
+  const float cp = -(ry * p.z);   /* perp  = fmaf(rx, uy, -(ry*ux)) */
+  const float ux = p.z, uy = p.w, L = q.x, hw = q.z;
+  auto along = [&](int i) { return fmaf(((float)i + 0.5f) - p.x, ux, ca); };
+  auto perp = [&](int i) { return fmaf(((float)i + 0.5f) - p.x, uy, cp); };
+  if (L < 0.0f) {
+    hi = lo - 1;
   } else {
-    /* thick line segment: !(along < 0 || along > L || |perp| > hw), each bound monotone in x */
-    float4 p = edges[R.e0], q = edges[R.e0 + 1];
-    const float ry = y - p.y;
-    const float ca = ry * p.w;      /* along = fmaf(rx, ux, ry*uy) */
-    const float cp = -(ry * p.z);   /* perp  = fmaf(rx, uy, -(ry*ux)) */
-    const float ux = p.z, uy = p.w, L = q.x, hw = q.z;
-    auto along = [&](int i) { return fmaf(((float)i + 0.5f) - p.x, ux, ca); };
-    auto perp = [&](int i) { return fmaf(((float)i + 0.5f) - p.x, uy, cp); };
-    if (L < 0.0f) {
+    /* along in [0, L] */
+    if (ux > 0.0f) {
+      lo = first_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
+      if (lo <= hi) hi = last_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
+    } else if (ux < 0.0f) {
+      hi = last_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
+      if (lo <= hi) lo = first_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
+    } else if (ca < 0.0f || ca > L) {
       hi = lo - 1;
-    } else {
-      /* along in [0, L] */
-      if (ux > 0.0f) {
-        lo = first_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
-        if (lo <= hi) hi = last_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
-      } else if (ux < 0.0f) {
-        hi = last_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
-        if (lo <= hi) lo = first_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
-      } else if (ca < 0.0f || ca > L) {
+    }
+    /* perp in [-hw, hw] */
+    if (lo <= hi) {
+      if (uy > 0.0f) {
+        lo = first_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
+        if (lo <= hi) hi = last_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
+      } else if (uy < 0.0f) {
+        hi = last_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
+        if (lo <= hi) lo = first_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
+      } else if (fabsf(cp) > hw) {
         hi = lo - 1;
-      }
-      /* perp in [-hw, hw] */
-      if (lo <= hi) {
-        if (uy > 0.0f) {
-          lo = first_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
-          if (lo <= hi) hi = last_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
-        } else if (uy < 0.0f) {
-          hi = last_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
-          if (lo <= hi) lo = first_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
-        } else if (fabsf(cp) > hw) {
-          hi = lo - 1;
-        }
       }
     }
   }
@@ -753,7 +729,8 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * batch : 0;
           const uint4* ptr =
               reinterpret_cast<const uint4*>(obs + ((plane + env) * frame_px + (size_t)Y * res_out + X0) * 12);
-          pre[v][0] = ptr[0]; pre[v][1] = ptr[1]; pre[v][2] = ptr[2];
+          /* streaming accesses: every byte of the stack is touched exactly once per step */
+          pre[v][0] = __ldcs(ptr); pre[v][1] = __ldcs(ptr + 1); pre[v][2] = __ldcs(ptr + 2);
         }
       }
       uint32_t col[NV][4];
@@ -781,9 +758,9 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           }
 #pragma unroll
           for (int i = 0; i < 4; i++) stack_push(&w[3 * i], col[v][i], fresh);
-          ptr[0] = make_uint4(w[0], w[1], w[2], w[3]);
-          ptr[1] = make_uint4(w[4], w[5], w[6], w[7]);
-          ptr[2] = make_uint4(w[8], w[9], w[10], w[11]);
+          __stcs(ptr, make_uint4(w[0], w[1], w[2], w[3]));
+          __stcs(ptr + 1, make_uint4(w[4], w[5], w[6], w[7]));
+          __stcs(ptr + 2, make_uint4(w[8], w[9], w[10], w[11]));
         }
       } else if (MODE == MG_OBS_LORES3EA) {
         /* bytes 0..2 = newest allo frame; bytes 3..11 = 3 ego frames, oldest first */
@@ -809,9 +786,9 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
             w[3 * i + 2] = (w2 >> 24) | (eg << 8);
           }
         }
-        ptr[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        ptr[1] = make_uint4(w[4], w[5], w[6], w[7]);
-        ptr[2] = make_uint4(w[8], w[9], w[10], w[11]);
+        __stcs(ptr, make_uint4(w[0], w[1], w[2], w[3]));
+        __stcs(ptr + 1, make_uint4(w[4], w[5], w[6], w[7]));
+        __stcs(ptr + 2, make_uint4(w[8], w[9], w[10], w[11]));
       } else if (MODE == MG_OBS_LORESCHW4E) {
         /* [B, 12, R, R]: plane c of frame f is channel 3f + c; 4 pixels = one u32 per plane */
         uint8_t* base = obs + (size_t)env * 12 * frame_px + (size_t)Y * res_out + X0;
