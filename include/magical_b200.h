@@ -201,7 +201,9 @@ typedef struct {
   int32_t reset_seed;   /* n_scenes > 1 with auto_reset: an env that finishes an episode draws its next
                            scene on the device as hash(reset_seed, env, resets so far) % n_scenes (the
                            reference re-randomises the layout on every reset, base_env.py:177-234) */
-  int32_t reserved_[8];
+  int32_t keep_scene;   /* 1: auto-reset restarts an env on the scene it is bound to (e.g. a mixed-task batch)
+                           instead of drawing a new pool entry */
+  int32_t reserved_[7];
 } mg_config_t;
 
 /* One environment's simulator state in host-readable form (parity tests). */
@@ -240,6 +242,15 @@ int64_t mg_obs_nbytes(const mg_handle* h);
  * int32[n] scene index per reset env (NULL => keep each env's current scene, initially 0).
  * Renders the first observation into the bound buffer (frame replicated over the stack). */
 int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* scene_ids);
+
+/* Scene pool maintenance for the randomised variants (the reference samples a fresh layout on every reset,
+ * base_env.py:177-234; here the host streams freshly sampled scenes into the pool while the GPU steps):
+ * mg_update_scenes overwrites pool entries [first, first + n) -- the caller must make sure that no environment is
+ * still playing them, e.g. by keeping them outside the draw range for at least one episode length;
+ * mg_set_draw_range restricts the entries an auto-reset draws from (n = 0: keep each env on its scene).
+ * New scenes must fit the capacities the handle reserved at mg_create (largest scene seen then). */
+int mg_update_scenes(mg_handle* h, int32_t first, int32_t n, const mg_scene_t* scenes);
+int mg_set_draw_range(mg_handle* h, int32_t first, int32_t n);
 
 /* One env-step for the whole batch: Robot.set_action + 10 x (Robot.update + Space.step)
  * + episode bookkeeping + score + render + stack (base_env.py:255-292).

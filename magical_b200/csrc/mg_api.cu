@@ -30,8 +30,8 @@ cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, c
 size_t mg_tpe_smem_bytes(const TpeLayout* L);
 size_t mg_tpe_spill_doubles_per_env(const TpeLayout* L);
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
-                             int n_scenes, uint32_t reset_seed, float* reward, uint8_t* done, float* score,
-                             cudaStream_t stream);
+                             int draw_first, int draw_count, uint32_t reset_seed, float* reward, uint8_t* done,
+                             float* score, cudaStream_t stream);
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
                             const int32_t* scene_ids, int first_time, cudaStream_t stream);
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
@@ -62,6 +62,7 @@ struct mg_handle {
   /* mg_step software pipeline: the batch is cut into chunks whose physics and raster kernels run on two
    * internal streams, staggered so that the raster of chunk c overlaps the physics of chunk c + 1 (the
    * physics is latency-bound at ~13 % issue utilisation, the raster issue-bound: they share SMs well) */
+  int draw_first, draw_count; /* pool entries an auto-reset draws from (mg_set_draw_range) */
   int n_chunks;
   cudaStream_t side[2];
   cudaEvent_t ev_start, ev_phys[2], ev_done[2];
@@ -79,6 +80,48 @@ static int fail(int code, const char* fmt, const char* detail) {
     cudaError_t e_ = (expr);                                                \
     if (e_ != cudaSuccess) return fail(MG_E_CUDA, #expr ": %s", cudaGetErrorString(e_)); \
   } while (0)
+
+/* what the rasteriser must reserve for one scene: polygon edges, window-space primitives, span-table rows */
+static const char* scene_raster_needs(const mg_scene_t& sc, int res_full, int* edges_out, int* rprims_out,
+                                      int* rows_out) {
+  const double S_full = (double)res_full / 2.04;
+  int edges = 0, rprims = 0, rows = 0;
+  for (int p = 0; p < sc.n_prims; p++) {
+    const mg_prim_t& pr = sc.prims[p];
+    edges += pr.nvert;
+    rprims += pr.kind == MG_PRIM_LINELOOP ? pr.nvert : 1;
+    /* span-table rows: a primitive is rigid, so in any camera it spans at most its diameter */
+    if (pr.kind == MG_PRIM_NGON) {
+      int r = (int)ceil(2.0 * pr.radius * S_full) + 8;
+      rows += r < res_full ? r : res_full;
+    } else if ((int)pr.vert0 + pr.nvert <= MG_MAX_DVERTS) {
+      const float(*dv)[2] = &sc.dverts[pr.vert0];
+      if (pr.kind == MG_PRIM_LINELOOP) {
+        for (int k = 0; k < pr.nvert; k++) {
+          int k2 = (k + 1) % pr.nvert;
+          double len = hypot((double)dv[k][0] - dv[k2][0], (double)dv[k][1] - dv[k2][1]);
+          int r = (int)ceil(len * S_full + pr.radius) + 8;
+          rows += r < res_full ? r : res_full;
+        }
+      } else {
+        double diam = 0.0;
+        for (int a = 0; a < pr.nvert; a++)
+          for (int b = a + 1; b < pr.nvert; b++) {
+            double d = hypot((double)dv[a][0] - dv[b][0], (double)dv[a][1] - dv[b][1]);
+            if (d > diam) diam = d;
+          }
+        int r = (int)ceil(diam * S_full) + 8;
+        rows += r < res_full ? r : res_full;
+      }
+    }
+    if (pr.kind == MG_PRIM_NGON && pr.nvert != 10 && pr.nvert != 20 && pr.nvert != 100)
+      return "NGON primitives must have 10, 20 or 100 sides";
+    if (pr.kind != MG_PRIM_NGON && (int)pr.vert0 + pr.nvert > MG_MAX_DVERTS) return "draw vertex range";
+  }
+  if (rprims > 192) return "too many draw primitives in one scene";
+  *edges_out = edges; *rprims_out = rprims; *rows_out = rows;
+  return nullptr;
+}
 
 extern "C" {
 
@@ -122,46 +165,13 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   int ecap = 64, scap = 64, rcap = 32;
   const int ss = cfg->obs_mode == MG_OBS_RAW ? 1 : 4;
   const int res_full = res_out * ss;
-  const double S_full = (double)res_full / 2.04;
   for (int i = 0; i < cfg->n_scenes; i++) {
     host[i].s = scenes[i];
     const char* why = mg_build_scene_aux(&scenes[i], &host[i].aux);
     if (why) return fail(MG_E_INVALID, "mg_create: scene rejected: %s", why);
     int edges = 0, rprims = 0, rows = 0;
-    for (int p = 0; p < scenes[i].n_prims; p++) {
-      const mg_prim_t& pr = scenes[i].prims[p];
-      edges += pr.nvert;
-      rprims += pr.kind == MG_PRIM_LINELOOP ? pr.nvert : 1;
-      /* span-table rows: a primitive is rigid, so in any camera it spans at most its diameter */
-      if (pr.kind == MG_PRIM_NGON) {
-        int r = (int)ceil(2.0 * pr.radius * S_full) + 8;
-        rows += r < res_full ? r : res_full;
-      } else if ((int)pr.vert0 + pr.nvert <= MG_MAX_DVERTS) {
-        const float(*dv)[2] = &scenes[i].dverts[pr.vert0];
-        if (pr.kind == MG_PRIM_LINELOOP) {
-          for (int k = 0; k < pr.nvert; k++) {
-            int k2 = (k + 1) % pr.nvert;
-            double len = hypot((double)dv[k][0] - dv[k2][0], (double)dv[k][1] - dv[k2][1]);
-            int r = (int)ceil(len * S_full + pr.radius) + 8;
-            rows += r < res_full ? r : res_full;
-          }
-        } else {
-          double diam = 0.0;
-          for (int a = 0; a < pr.nvert; a++)
-            for (int b = a + 1; b < pr.nvert; b++) {
-              double d = hypot((double)dv[a][0] - dv[b][0], (double)dv[a][1] - dv[b][1]);
-              if (d > diam) diam = d;
-            }
-          int r = (int)ceil(diam * S_full) + 8;
-          rows += r < res_full ? r : res_full;
-        }
-      }
-      if (pr.kind == MG_PRIM_NGON && pr.nvert != 10 && pr.nvert != 20 && pr.nvert != 100)
-        return fail(MG_E_INVALID, "mg_create: NGON primitives must have 10, 20 or 100 sides%s", "");
-      if (pr.kind != MG_PRIM_NGON && (int)pr.vert0 + pr.nvert > MG_MAX_DVERTS)
-        return fail(MG_E_INVALID, "mg_create: draw vertex range%s", "");
-    }
-    if (rprims > 192) return fail(MG_E_INVALID, "mg_create: too many draw primitives in one scene%s", "");
+    const char* bad = scene_raster_needs(scenes[i], res_full, &edges, &rprims, &rows);
+    if (bad) return fail(MG_E_INVALID, "mg_create: %s", bad);
     if (edges > ecap) ecap = edges;
     if (rows > scap) scap = rows;
     if (rprims > rcap) rcap = rprims;
@@ -201,6 +211,8 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
     if (v == 128 || v == 512) h->block_threads = v;
   }
   h->obs_bytes = obs_bytes_for(cfg, res_out);
+  h->draw_first = 0;
+  h->draw_count = cfg->keep_scene ? 0 : cfg->n_scenes;
   /* K1 variant: every MAGICAL scene has the canonical robot + drag-jointed blocks structure and runs one
    * environment per thread; anything else (hand-built scenes) falls back to the cooperative kernel */
   h->use_tpe = 1;
@@ -366,7 +378,7 @@ static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_de
   else
     CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads,
                                h->stream));
-  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, h->cfg.auto_reset, 0, h->cfg.n_scenes,
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, h->cfg.auto_reset, 0, h->draw_first, h->draw_count,
                             (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->stream));
   h->launches += 2;
   return MG_OK;
@@ -393,7 +405,7 @@ static int step_pipelined(mg_handle* h, const int32_t* actions_dev, float* rewar
     CUDA_TRY(mg_launch_physics_tpe(h->d_states, h->d_scenes, actions_dev, env0, count, &h->tpe, h->d_spill, h->d_scratch,
                                    st));
     CUDA_TRY(cudaEventRecord(h->ev_phys[c & 1], st));
-    CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, env0, count, h->cfg.auto_reset, 0, h->cfg.n_scenes,
+    CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, env0, count, h->cfg.auto_reset, 0, h->draw_first, h->draw_count,
                               (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, st));
     CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, B, h->res_out, h->ecap, h->scap, h->rcap,
                               0, env0, count, st));
@@ -429,7 +441,7 @@ int mg_render(mg_handle* h) {
 int mg_score(mg_handle* h, float* score_dev) {
   if (!h || !score_dev) return fail(MG_E_INVALID, "mg_score: null argument%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, 0, 1, 1, 0u, nullptr, nullptr, score_dev, h->stream));
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, 0, 1, 0, 1, 0u, nullptr, nullptr, score_dev, h->stream));
   h->launches++;
   return MG_OK;
 }
@@ -483,6 +495,45 @@ int mg_set_pose(mg_handle* h, int32_t env, int32_t body, double x, double y, dou
   EnvState* st = h->d_states + env;
   CUDA_TRY(cudaMemcpy(&st->P[body], &P, sizeof(P), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(&st->R[body], &R, sizeof(R), cudaMemcpyHostToDevice));
+  return MG_OK;
+}
+
+int mg_update_scenes(mg_handle* h, int32_t first, int32_t n, const mg_scene_t* scenes) {
+  if (!h || !scenes) return fail(MG_E_INVALID, "mg_update_scenes: null argument%s", "");
+  if (first < 0 || n <= 0 || first + n > h->cfg.n_scenes) return fail(MG_E_INVALID, "mg_update_scenes: range%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const int ss = h->cfg.obs_mode == MG_OBS_RAW ? 1 : 4;
+  std::vector<DeviceScene> host(n);
+  for (int i = 0; i < n; i++) {
+    host[i].s = scenes[i];
+    const char* why = mg_build_scene_aux(&scenes[i], &host[i].aux);
+    if (why) return fail(MG_E_INVALID, "mg_update_scenes: scene rejected: %s", why);
+    int edges = 0, rprims = 0, rows = 0;
+    const char* bad = scene_raster_needs(scenes[i], h->res_out * ss, &edges, &rprims, &rows);
+    if (bad) return fail(MG_E_INVALID, "mg_update_scenes: %s", bad);
+    /* the kernels' shared-memory layouts were sized at mg_create for the largest scene seen then */
+    if (edges > h->ecap || rows > h->scap || rprims > h->rcap)
+      return fail(MG_E_INVALID, "mg_update_scenes: scene needs more rasteriser capacity than the handle reserved%s", "");
+    if (h->use_tpe) {
+      const mg_scene_aux_t& ax = host[i].aux;
+      const int con_words = h->tpe.scratch_global ? (h->tpe.words - h->tpe.off_con) : (h->tpe.off_it - h->tpe.off_con);
+      if (!ax.tpe_ok || ax.tpe_nslots > h->tpe.nslots || ax.tpe_nblocks > h->tpe.nblocks ||
+          scenes[i].n_cgroups * 3 > con_words || (scenes[i].n_bpairs + 1) / 2 + h->tpe.nitems > h->tpe.scratch_u32)
+        return fail(MG_E_INVALID, "mg_update_scenes: scene exceeds the physics layout the handle was created with%s", "");
+    }
+  }
+  /* environments bound to these entries must have finished their episodes (caller's contract, see header) */
+  CUDA_TRY(cudaMemcpyAsync(h->d_scenes + first, host.data(), sizeof(DeviceScene) * (size_t)n, cudaMemcpyHostToDevice,
+                           h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return MG_OK;
+}
+
+int mg_set_draw_range(mg_handle* h, int32_t first, int32_t n) {
+  if (!h) return fail(MG_E_INVALID, "mg_set_draw_range: null handle%s", "");
+  if (first < 0 || n < 0 || first + n > h->cfg.n_scenes) return fail(MG_E_INVALID, "mg_set_draw_range: range%s", "");
+  h->draw_first = first;
+  h->draw_count = n;
   return MG_OK;
 }
 

@@ -237,7 +237,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) { /* lowbias32 integer has
 }
 
 __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, int env0, int count,
-                         int auto_reset, int mode, int n_scenes, uint32_t reset_seed, float* __restrict__ reward,
+                         int auto_reset, int mode, int draw_first, int draw_count, uint32_t reset_seed,
+                         float* __restrict__ reward,
                          uint8_t* __restrict__ done, float* __restrict__ score) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= count) return;
@@ -270,10 +271,11 @@ __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __res
   if (score) score[env] = (float)s;
   if (d && auto_reset) {
     int scene = st.scene;
-    if (n_scenes > 1) {
-      /* randomised variants: the next episode plays a freshly drawn scene of the pre-sampled pool */
+    if (draw_count > 0 && (draw_count > 1 || draw_first != scene)) {
+      /* randomised variants: the next episode plays a freshly drawn scene of the pool's current draw range */
       const int resets = ++st.resets;
-      scene = (int)(mix32(mix32(reset_seed ^ mix32((uint32_t)env)) + (uint32_t)resets) % (uint32_t)n_scenes);
+      scene = draw_first +
+              (int)(mix32(mix32(reset_seed ^ mix32((uint32_t)env)) + (uint32_t)resets) % (uint32_t)draw_count);
     }
     reset_state(st, scenes + scene, scene);
   }
@@ -296,11 +298,12 @@ __global__ void k_reset(EnvState* __restrict__ states, const DeviceScene* __rest
 }
 
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
-                             int n_scenes, uint32_t reset_seed, float* reward, uint8_t* done, float* score,
-                             cudaStream_t stream) {
+                             int draw_first, int draw_count, uint32_t reset_seed, float* reward, uint8_t* done,
+                             float* score, cudaStream_t stream) {
   int threads = 128;
   k_finish<<<(count + threads - 1) / threads, threads, 0, stream>>>(states, scenes, env0, count, auto_reset, mode,
-                                                                    n_scenes, reset_seed, reward, done, score);
+                                                                    draw_first, draw_count, reset_seed, reward, done,
+                                                                    score);
   return cudaGetLastError();
 }
 

@@ -81,7 +81,7 @@ scene_dt = np.dtype([
 config_dt = np.dtype([('device', 'i4'), ('batch', 'i4'), ('n_scenes', 'i4'),
                       ('obs_mode', 'i4'), ('res', 'i4'), ('auto_reset', 'i4'),
                       ('fast_math', 'i4'), ('reset_seed', 'i4'),
-                      ('reserved_', 'i4', 8)], align=True)
+                      ('keep_scene', 'i4'), ('reserved_', 'i4', 7)], align=True)
 
 state_dt = np.dtype([
     ('n_bodies', 'i4'), ('n_joints', 'i4'), ('n_contacts', 'i4'),

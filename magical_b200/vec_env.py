@@ -42,7 +42,7 @@ class MagicalVecEnv:
 
     def __init__(self, task, batch, preproc=None, device=0, auto_reset=True,
                  n_scenes=1, seed=None, scenes=None, stream=None,
-                 alloc_obs=True):
+                 alloc_obs=True, keep_scene=False):
         import torch
         if not torch.cuda.is_available():
             raise _native.NativeError(
@@ -70,7 +70,8 @@ class MagicalVecEnv:
                                   n_scenes=self.n_scenes, obs_mode=self.mode,
                                   res=res, auto_reset=int(self.auto_reset),
                                   fast_math=0,
-                                  reset_seed=int(self.rng.randint(1 << 31)))
+                                  reset_seed=int(self.rng.randint(1 << 31)),
+                                  keep_scene=int(bool(keep_scene)))
         import ctypes
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
@@ -113,6 +114,37 @@ class MagicalVecEnv:
             sid_p = scene_ids.ctypes.data
         _native.check(self._lib.mg_reset(self._h, ids_p, n, sid_p))
         return self.obs
+
+    # -- scene pool maintenance (randomised variants) ----------------------
+    def update_scenes(self, first, scenes):
+        """Overwrite pool entries [first, first + len(scenes)); no environment
+        may still be playing them (keep them outside the draw range for one
+        episode length first)."""
+        scenes = np.ascontiguousarray(np.stack(scenes)).astype(sc.scene_dt,
+                                                                copy=False)
+        _native.check(self._lib.mg_update_scenes(
+            self._h, int(first), len(scenes), scenes.ctypes.data))
+        self.scenes[first:first + len(scenes)] = scenes
+
+    def set_draw_range(self, first, count):
+        """Pool entries an auto-reset draws from (count 0: keep the scene)."""
+        _native.check(self._lib.mg_set_draw_range(self._h, int(first),
+                                                  int(count)))
+        self._draw = (int(first), int(count))
+
+    def refresh_pool(self):
+        """Double-buffered pool streaming: sample fresh scenes into the half of
+        the pool that is currently NOT drawn from, then make it the draw range.
+        Call at most once per episode length (environments still playing the
+        other half finish within one episode).  Returns the new draw range."""
+        half = self.n_scenes // 2
+        assert half >= 1, 'refresh_pool needs a pool of at least 2 scenes'
+        first, _ = getattr(self, '_draw', (0, self.n_scenes))
+        new_first = half if first == 0 else 0
+        self.update_scenes(new_first, [self.task.build_scene()
+                                       for _ in range(half)])
+        self.set_draw_range(new_first, half)
+        return new_first, half
 
     def step(self, actions):
         """actions: int32 CUDA tensor [batch] (other int tensors / arrays are

@@ -427,3 +427,47 @@ def test_soak_contact_rich_batch_has_no_overflow(built):
         most = max(most, int(st['n_contacts']))
     assert most >= 4
     venv.close()
+
+
+def test_pool_streaming_and_keep_scene(built):
+    """mg_update_scenes / mg_set_draw_range: fresh host-sampled scenes are
+    streamed into the idle half of the pool and become the draw range; after
+    the next auto-reset every environment plays one of the NEW scenes, bit-exact
+    against the oracle.  keep_scene pins environments to their scene."""
+    import torch
+    import magical_b200 as magical
+    from magical_b200.vec_env import MagicalVecEnv
+    from oracle_lib import OracleEnv
+    env_id, batch = 'MoveToRegion-TestAll-LoRes4E-v0', 32
+    venv = magical.make_vec(env_id, batch, auto_reset=True, n_scenes=8, seed=2)
+    venv.set_draw_range(0, 4)
+    venv.reset(scene_ids=np.arange(batch) % 4)
+    old = venv.scenes.copy()
+    first, count = venv.refresh_pool()
+    assert (first, count) == (4, 4)
+    assert not np.array_equal(old[4:], venv.scenes[4:])
+    rng = np.random.RandomState(0)
+    for t in range(40):                      # one episode: everyone resets
+        venv.step(torch.from_numpy(rng.randint(0, 18, size=batch).astype(np.int32)).cuda())
+    scenes_now = [int(venv.get_state(e)['scene']) for e in range(batch)]
+    assert all(4 <= s < 8 for s in scenes_now)
+    e = 5
+    orc = OracleEnv(venv.scenes[scenes_now[e]], det_sincos=True)
+    for t in range(15):
+        acts = rng.randint(0, 18, size=batch).astype(np.int32)
+        venv.step(torch.from_numpy(acts).cuda())
+        orc.step(int(acts[e]))
+    st, ost = venv.get_state(e), orc.state()
+    nb = int(st['n_bodies'])
+    assert np.array_equal(st['pos'][:nb], ost['pos'][:nb])
+    venv.close()
+    # keep_scene: a mixed pool where every env stays on its own scene
+    task, spec = magical.make_task(env_id)
+    task.seed(9)
+    venv = MagicalVecEnv(task, 8, preproc=spec.preproc, auto_reset=True,
+                         n_scenes=4, keep_scene=True)
+    venv.reset(scene_ids=np.arange(8) % 4)
+    for t in range(41):
+        venv.step(torch.from_numpy(rng.randint(0, 18, size=8).astype(np.int32)).cuda())
+    assert [int(venv.get_state(i)['scene']) for i in range(8)] == list(np.arange(8) % 4)
+    venv.close()
