@@ -59,6 +59,7 @@ struct RPrim {
   int16_t col0, col1;   /* sample columns of the bounding box (inclusive) */
   int32_t span0;        /* offset of this primitive's rows in the span table */
   float sgn;            /* winding sign of the window-space polygon */
+  int32_t tile0;        /* offset of this primitive's (primitive, tile row) work items in the binning pass */
   float ymin, ymax;     /* vertical extent of the window-space vertices */
 };
 
@@ -323,24 +324,30 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
    * can bound: row j is bounded by an edge only if j + 0.5 lies within one sample of the edge's own
    * y-extent (the polygon is convex, so edges further away hold with a margin far above fp32 rounding) */
   if (tid < 32) {
-    int off = 0;
+    const int TSd = (res_out / RGRID) * SS; /* samples per tile side */
+    int off = 0, toff = 0;
     for (int base = 0; base < nrp; base += 32) {
       int p = base + tid;
       int nr = (p < nrp) ? vs.prims[p].nrows : 0;
-      int incl = nr;
+      int r0 = (p < nrp) ? vs.prims[p].row0 : 0;
+      /* tile rows the primitive's sample rows touch = its work items in the binning pass (F) */
+      int nt_rows = (nr > 0) ? (min((r0 + nr - 1) / TSd, RGRID - 1) - r0 / TSd + 1) : 0;
+      int incl = nr, tincl = nt_rows;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (tid >= d) incl += t;
+        int t = __shfl_up_sync(0xffffffffu, incl, d), tt = __shfl_up_sync(0xffffffffu, tincl, d);
+        if (tid >= d) { incl += t; tincl += tt; }
       }
       if (p < nrp) {
         int start = off + incl - nr;
         if (start + nr > scap) { vs.prims[p].nrows = 0; nr = 0; } /* cannot happen with the host's bound */
         vs.prims[p].span0 = start;
+        vs.prims[p].tile0 = toff + tincl - nt_rows;
       }
       off += __shfl_sync(0xffffffffu, incl, 31);
+      toff += __shfl_sync(0xffffffffu, tincl, 31);
     }
-    if (tid == 0) s_misc[2] = off > scap ? scap : off;
+    if (tid == 0) { s_misc[2] = off > scap ? scap : off; s_misc[6] = toff; }
   }
   for (int v = tid; v < nv; v += nt) {
     int lo = 0, hi = np - 1;
@@ -484,10 +491,15 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   __syncthreads();
   /* F: tile bins from the spans: one work item per (primitive, tile row) */
   const int TS = (res_out / RGRID) * SS; /* samples per tile side */
-  for (int w = tid; w < nrp * RGRID; w += nt) {
-    int p = w / RGRID, ty = w % RGRID;
+  const int npairs = s_misc[6];
+  for (int w = tid; w < npairs; w += nt) {
+    /* the primitive owning item w: last one whose tile0 is <= w (primitives without rows share offsets) */
+    int lo = 0, hi = nrp - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (vs.prims[mid].tile0 <= w) lo = mid; else hi = mid - 1; }
+    const int p = lo;
     const RPrim& R = vs.prims[p];
     if (R.nrows == 0) continue;
+    const int ty = (int)R.row0 / TS + (w - R.tile0);
     int ja = ty * TS, jb = ja + TS - 1;
     int a = max(ja, (int)R.row0), b = min(jb, R.row0 + R.nrows - 1);
     if (a > b) continue;
@@ -530,7 +542,9 @@ __device__ __forceinline__ uint32_t finish_colour(uint32_t sr, uint32_t sg, uint
 template <int SS>
 __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int tile, int cover, uint32_t words,
                                        float px_scale, uint32_t out[4]) {
-  constexpr uint32_t FULLM = (SS == 4) ? 0xFFFFu : 1u;
+  /* SS == 4: a pixel's 16 samples sit in a 32-bit mask as  row0 -> bits 0..3, row2 -> 4..7, row1 -> 16..19,
+   * row3 -> 20..23  (two packed 16-sample strips per word, so a pixel's mask is two shift+and pairs) */
+  constexpr uint32_t FULLM = (SS == 4) ? 0x00FF00FFu : 1u;
   uint32_t unres[4] = {FULLM, FULLM, FULLM, FULLM};
   uint32_t sr[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
   const uint32_t* tm = vs.tiles + tile * vs.rwords;
@@ -553,24 +567,26 @@ __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int t
       } else {
 #pragma unroll
         for (int i = 0; i < 4; i++) m[i] = 0u;
+        uint32_t strips[SS]; /* per sample row: bit c = sample column x0 + c is covered */
 #pragma unroll
         for (int r = 0; r < SS; r++) {
+          strips[r] = 0u;
           int row = y0 + r - R.row0;
           if (row >= 0 && row < R.nrows) {
             short2 sp = vs.spans[R.span0 + row];
             /* columns of the 4*SS-sample strip covered by this row */
             int l = max((int)sp.x - x0, 0), h = min((int)sp.y - x0, 4 * SS - 1);
-            if (l <= h) {
-              uint32_t strip = (0xFFFFFFFFu >> (31 - (h - l))) << l; /* bit c = sample column x0 + c */
-              if (SS == 4) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) m[i] |= ((strip >> (4 * i)) & 0xFu) << (4 * r);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; i++) m[i] |= (strip >> i) & 1u;
-              }
-            }
+            if (l <= h) strips[r] = (0xFFFFFFFFu >> (31 - (h - l))) << l;
           }
+        }
+        if (SS == 4) {
+          const uint32_t v01 = strips[0] | (strips[1 % SS] << 16), v23 = strips[2 % SS] | (strips[3 % SS] << 16);
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            m[i] = ((v01 >> (4 * i)) & 0x000F000Fu) | (((v23 >> (4 * i)) & 0x000F000Fu) << 4);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) m[i] = (strips[0] >> i) & 1u;
         }
         const bool stippled = (R.rgb >> 24) != 0;
 #pragma unroll
@@ -584,7 +600,10 @@ __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int t
             while (mm) {
               int s = __ffs(mm) - 1;
               mm &= mm - 1;
-              float x = ((float)(x0 + SS * i + (s % SS))) + 0.5f, y = ((float)(y0 + (s / SS))) + 0.5f;
+              /* bit -> (column, row) of the sample inside the pixel, see the mask layout above */
+              const int sc_ = (SS == 4) ? (s & 3) : 0;
+              const int sr_ = (SS == 4) ? (((s >> 4) & 1) + 2 * ((s >> 2) & 1)) : 0;
+              float x = ((float)(x0 + SS * i + sc_)) + 0.5f, y = ((float)(y0 + sr_)) + 0.5f;
               float along = fmaf(x - pp.x, pp.z, (y - pp.y) * pp.w);
               int bit = ((int)floorf((q.y + along) / px_scale)) & 15;
               keep |= ((stipple >> bit) & 1u) << s;
