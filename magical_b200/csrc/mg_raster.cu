@@ -39,6 +39,7 @@
 #define RGRID 12           /* tiles per side */
 #define RMAXP 192          /* window-space primitives (draw prims + expanded line segments) */
 #define RWORDS (RMAXP / 32)
+#define RLONG 512          /* capacity of the compact long-edge list (>= 2 * MG_MAX_PRIMS + 2) */
 #define RSHORT 12          /* polygon edges bounding fewer rows than this are processed one edge per lane */
 #define BG_R 231
 #define BG_G 231
@@ -393,7 +394,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
    * y-extent are empty), thick line segments are solved directly per row */
   const int nwarp = nt >> 5, wid = tid >> 5, lane = tid & 31;
   if (wid == 0) {
-    int off = 0;
+    int off = 0, nlong = 0;
     for (int base = 0; base < nv; base += 32) {
       int v = base + lane;
       int c = (v < nv) ? __float_as_int(vs.eaux[v].w) : 0;
@@ -403,10 +404,17 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         int t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
       }
-      if (v < nv) vs.eaux[v].w = __int_as_float(off + incl - c);
+      const int start = off + incl - c;
+      if (v < nv) vs.eaux[v].w = __int_as_float(start);
       off += __shfl_sync(0xffffffffu, incl, 31);
+      /* compact list of the edges that own items: item offset << 10 | edge (most table entries -- sides of the
+       * many-gons, line vertices -- own none and would otherwise be walked over by every lane) */
+      const unsigned has = __ballot_sync(0xffffffffu, c > 0);
+      const int k = nlong + __popc(has & ((1u << lane) - 1u));
+      if (c > 0 && k < RLONG) s_off[k] = (start << 10) | v;
+      nlong += __popc(has);
     }
-    if (lane == 0) s_misc[3] = off;
+    if (lane == 0) { s_misc[3] = off; s_misc[5] = nlong; }
   } else {
     for (int p = wid - 1; p < nrp; p += nwarp - 1) {
       const RPrim R = vs.prims[p];
@@ -467,8 +475,20 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     const int chunk = ((n_items + nwarp - 1) / nwarp + 31) & ~31;
     const int it_end = min((wid + 1) * chunk, n_items);
     int it = wid * chunk + lane;
-    if (it < it_end) {
-      /* the edge holding item `it`: last edge whose offset is <= it (edges with no items share offsets) */
+    const int nlong = s_misc[5];
+    if (it < it_end && nlong <= RLONG && nv <= 1024) {
+      /* the long edge holding item `it`: last list entry whose offset is <= it */
+      int lo = 0, hi = nlong - 1;
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((s_off[mid] >> 10) <= it) lo = mid; else hi = mid - 1; }
+      int k = lo;
+      for (; it < it_end; it += 32) {
+        while (k + 1 < nlong && (s_off[k + 1] >> 10) <= it) k++;
+        const int e = s_off[k] & 1023;
+        const float4 X = vs.eaux[e];
+        fold(vs.edges[e], X, __float_as_int(X.z) + (it - __float_as_int(X.w)));
+      }
+    } else if (it < it_end) {
+      /* list overflow (never with the registered scenes): walk the full edge table */
       int lo = 0, hi = nv - 1;
       while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (__float_as_int(vs.eaux[mid].w) <= it) lo = mid; else hi = mid - 1; }
       int e = lo;
@@ -658,7 +678,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   constexpr int NV = (MODE == MG_OBS_LORES3EA) ? 2 : 1;
   constexpr int NPASS = SEQ ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_off[2 * MG_MAX_PRIMS + 2];
+  __shared__ int s_off[RLONG]; /* prefix tables of phase A..D (2 * MG_MAX_PRIMS + 2 ints), then the long-edge list */
   __shared__ int s_misc[8];
   const int env = env0 + blockIdx.x; /* this launch covers environments [env0, env0 + gridDim.x) */
   if (env >= batch) return;
