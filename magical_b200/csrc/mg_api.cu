@@ -252,7 +252,7 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
       (e = cudaMalloc(&h->d_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_scene_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
       (h->use_tpe && mg_tpe_spill_doubles_per_env(&h->tpe) > 0 &&
-       (e = cudaMalloc(&h->d_spill, sizeof(double) * mg_tpe_spill_doubles_per_env(&h->tpe) * (size_t)cfg->batch)) !=
+       (e = cudaMalloc(&h->d_spill, sizeof(double) * mg_tpe_spill_doubles_per_env(&h->tpe) * ((size_t)cfg->batch + 64))) !=
            cudaSuccess) ||
       (h->use_tpe && h->tpe.scratch_global &&
        (e = cudaMalloc(&h->d_scratch, sizeof(uint32_t) * (size_t)h->tpe.scratch_u32 * ((size_t)cfg->batch + 32))) !=

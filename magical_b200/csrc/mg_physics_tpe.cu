@@ -29,7 +29,10 @@ k_physics_tpe(EnvState* __restrict__ states, const DeviceScene* __restrict__ sce
   T.wf = reinterpret_cast<float*>(tpe_words) + threadIdx.x;
   T.wh = reinterpret_cast<uint16_t*>(tpe_words) + threadIdx.x;
   T.L = L;
-  T.spill = spill ? spill + (size_t)env * (size_t)((TPE_MAX_CONTACTS - L.kcon) * TPE_CON_WORDS) : nullptr;
+  /* spill record of this launch slot's block, interleaved like the private words */
+  T.spill = spill ? spill + (size_t)(env0 / TPE_THREADS + blockIdx.x) * (size_t)((TPE_MAX_CONTACTS - L.kcon) * TPE_CON_WORDS) *
+                                TPE_THREADS + threadIdx.x
+                  : nullptr;
   T.slotmap = 0;
   T.static_slot = 0;
   /* scratch records are indexed by launch slot (not by the clamped env), so every lane has its own */

@@ -137,7 +137,7 @@ struct Tpe {
   uint16_t* sepp; /* separation cache, same stride */
   int it_st, it_lane;
   TpeLayout L;
-  double* spill; /* [TPE_MAX_CONTACTS - kcon][TPE_CON_WORDS] contiguous, or null */
+  double* spill; /* this lane's column of the block's [TPE_MAX_CONTACTS - kcon][TPE_CON_WORDS][S] spill record, or null */
   uint64_t slotmap;
   int static_slot;
   MG_HDM double& V(int s, int k) const { return wd[(s * 3 + k) * S]; }
@@ -165,17 +165,19 @@ struct Tpe {
   }
 };
 
-/* reference to the words of contact c (private words or spill area) */
+/* reference to the words of contact c (private words or spill area).  The spill area uses the same
+ * [word][lane] interleaving as the private words (one record per 32-environment block), so word k of a contact
+ * is always S elements after word k - 1 and the accesses compile to immediate offsets. */
+template <int S>
 struct TpeCon {
   double* p;
-  int st;
-  MG_HDM double& operator[](int k) const { return p[k * st]; }
+  MG_HDM double& operator[](int k) const { return p[k * S]; }
 };
 template <int S>
-MG_HD TpeCon tpe_con(const Tpe<S>& T, int c) {
-  TpeCon r;
-  if (c < T.L.kcon) { r.p = &T.wd[(T.L.off_con + c * TPE_CON_WORDS) * S]; r.st = S; }
-  else { r.p = T.spill + (c - T.L.kcon) * TPE_CON_WORDS; r.st = 1; }
+MG_HD TpeCon<S> tpe_con(const Tpe<S>& T, int c) {
+  TpeCon<S> r;
+  if (c < T.L.kcon) r.p = &T.wd[(T.L.off_con + c * TPE_CON_WORDS) * S];
+  else r.p = T.spill + (size_t)((c - T.L.kcon) * TPE_CON_WORDS) * S;
   return r;
 }
 /* contact words: 0,1 r1 | 2,3 r2 | 4,5 n | 6 nMass | 7 tMass | 8 bias | 9 jn | 10 jt | 11 jb | 12 u | 13 ids */
@@ -707,7 +709,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         if (q < m.count) {
-          TpeCon C = tpe_con(T, ncon + q);
+          TpeCon<S> C = tpe_con(T, ncon + q);
           d2 r1 = dsub(m.p1[q], pa), r2 = dsub(m.p2[q], pb);
           C[0] = r1.x; C[1] = r1.y; C[2] = r2.x; C[3] = r2.y; C[4] = m.n.x; C[5] = m.n.y;
           C[9] = jn[q]; C[10] = jt[q]; C[12] = u;
@@ -871,7 +873,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
 
     /* ---- contact prestep */
     for (int c = 0; c < ncon; c++) {
-      TpeCon C = tpe_con(T, c);
+      TpeCon<S> C = tpe_con(T, c);
       const unsigned long long ids = tpe_unpack_ids(C[13]);
       const int ba = (int)((ids >> 48) & 0x1F), bb = (int)((ids >> 53) & 0x1F);
       const double ma = ba < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[ba].m_inv) : 0.0;
@@ -966,7 +968,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
 
     /* ---- warm start (cpArbiterApplyCachedImpulse, then the joints' applyCachedImpulse; dt_coef = 1) */
     for (int c = 0; c < ncon; c++) {
-      TpeCon C = tpe_con(T, c);
+      TpeCon<S> C = tpe_con(T, c);
       const unsigned long long ids = tpe_unpack_ids(C[13]);
       if ((ids >> 58) & 1ull) continue; /* first contact of the pair */
       const int ba = (int)((ids >> 48) & 0x1F), bb = (int)((ids >> 53) & 0x1F);
@@ -1024,7 +1026,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     /* ---- solver iterations (cpArbiterApplyImpulse for every arbiter, then every joint) */
     for (int it = 0; it < MG_ITERATIONS; ++it) {
       for (int c = 0; c < ncon; c++) {
-        TpeCon C = tpe_con(T, c);
+        TpeCon<S> C = tpe_con(T, c);
         const unsigned long long ids = tpe_unpack_ids(C[13]);
         const int ba = (int)((ids >> 48) & 0x1F), bb = (int)((ids >> 53) & 0x1F);
         const int sa_ = T.slot(ba), sb_ = T.slot(bb);
@@ -1147,7 +1149,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
       if (ncon > 0)
         for (int q = tot - ncon - 1; q >= 0; q--) G->cache[q + ncon] = G->cache[q]; /* shift up, back to front */
       for (int c = 0; c < ncon; c++) {
-        TpeCon C = tpe_con(T, c);
+        TpeCon<S> C = tpe_con(T, c);
         const unsigned long long ids = tpe_unpack_ids(C[13]);
         CEntry e;
         e.a = (uint8_t)((ids >> 32) & 0xFF); e.b = (uint8_t)((ids >> 40) & 0xFF); e.used = 0; e.pad_ = 0;
