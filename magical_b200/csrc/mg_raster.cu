@@ -40,7 +40,9 @@
 #define RMAXP 192          /* window-space primitives (draw prims + expanded line segments) */
 #define RWORDS (RMAXP / 32)
 #define RLONG 512          /* capacity of the compact long-edge list (>= 2 * MG_MAX_PRIMS + 2) */
+#ifndef RSHORT
 #define RSHORT 12          /* polygon edges bounding fewer rows than this are processed one edge per lane */
+#endif
 #define BG_R 231
 #define BG_G 231
 #define BG_B 234
