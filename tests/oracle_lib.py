@@ -147,3 +147,27 @@ def downsample4(img):
     out = np.zeros((n, n, 3), dtype=np.uint8)
     lib().mgo_downsample4(img.ctypes.data, n, out.ctypes.data)
     return out
+
+
+def rollout_scores(job):
+    """Worker for the score sweeps: job = (scene_records, actions[T, n]); steps
+    one oracle per column through its whole action stream (physics + score,
+    no render) and returns (score at the done step [n] f32, step of done [n],
+    final positions [n, MAX_BODIES, 2])."""
+    scenes, actions = job
+    n = actions.shape[1]
+    score = np.full(n, np.nan, dtype=np.float32)
+    done_at = np.full(n, -1, dtype=np.int32)
+    pos = None
+    for e in range(n):
+        orc = OracleEnv(scenes[e], det_sincos=True)
+        for t in range(actions.shape[0]):
+            _, d, s = orc.step(int(actions[t, e]))
+            if d and done_at[e] < 0:
+                done_at[e], score[e] = t, np.float32(s)
+        st = orc.state()
+        if pos is None:
+            pos = np.zeros((n,) + st['pos'].shape)
+        pos[e] = st['pos']
+        orc.close()
+    return score, done_at, pos

@@ -80,3 +80,61 @@ def test_two_half_handles_equal_one_full_handle(built):
                        torch.cat([p[3]['eval_score'] for p in parts]))
     for v in (full, *halves):
         v.close()
+
+
+SWEEP = [(name + '-Demo-LoRes4E-v0', 0) for name in (
+    'MoveToCorner', 'MoveToRegion', 'MatchRegions', 'MakeLine', 'FindDupe',
+    'FixColour', 'ClusterColour', 'ClusterShape')] + [
+    ('MatchRegions-TestAll-LoRes4E-v0', 250),
+    ('ClusterColour-TestAll-LoRes4E-v0', 125),
+]
+
+
+@pytest.mark.parametrize('env_id,n_scenes', SWEEP)
+def test_score_sweep_1000_episodes(built, env_id, n_scenes):
+    """end-of-episode scores, done steps and final poses of
+    1000 random-action episodes per task, CUDA against the oracle (stepped on
+    all host cores), exact.  The two randomised variants run 1000 episodes
+    over a pool of distinct sampled layouts."""
+    import multiprocessing as mp
+    import os
+    import torch
+    import magical_b200 as magical
+    from oracle_lib import rollout_scores
+    batch = 1000
+    kw = dict(n_scenes=n_scenes, seed=5) if n_scenes else {}
+    venv = magical.make_vec(env_id, batch, auto_reset=False, **kw)
+    scene_ids = np.arange(batch) % max(n_scenes, 1)
+    venv.reset(scene_ids=scene_ids) if n_scenes else venv.reset()
+    n_steps = venv.max_episode_steps
+    rng = np.random.RandomState(101)
+    acts = _actions(rng, n_steps, batch, batch)
+    # oracle first (forked workers never touch CUDA)
+    chunk = 25
+    jobs = [([venv.scenes[scene_ids[e]] for e in range(lo, lo + chunk)],
+             acts[:, lo:lo + chunk]) for lo in range(0, batch, chunk)]
+    with mp.get_context('fork').Pool(min(os.cpu_count() or 1, 32)) as pool:
+        res = pool.map(rollout_scores, jobs)
+    o_score = np.concatenate([r[0] for r in res])
+    o_done = np.concatenate([r[1] for r in res])
+    o_pos = np.concatenate([r[2] for r in res])
+    score = np.full(batch, np.nan, dtype=np.float32)
+    done_at = np.full(batch, -1, dtype=np.int32)
+    for t in range(n_steps):
+        rew, done, info = venv.step_physics(torch.from_numpy(acts[t]).cuda())
+        d = done.cpu().numpy().astype(bool) & (done_at < 0)
+        done_at[d] = t
+        score[d] = info['eval_score'].cpu().numpy()[d]
+    assert np.array_equal(done_at, o_done)
+    assert (done_at == n_steps - 1).all()
+    assert np.array_equal(score, o_score), \
+        np.flatnonzero(score != o_score)[:10]
+    for e in range(batch):
+        st = venv.get_state(e)
+        nb = int(st['n_bodies'])
+        assert int(st['overflow']) == 0
+        assert np.array_equal(st['pos'][:nb], o_pos[e][:nb]), (env_id, e)
+    # the sweep must exercise the score function, not just zeros
+    if env_id.startswith('MoveToCorner') or n_scenes:
+        assert len(np.unique(score)) > 1, np.unique(score)
+    venv.close()
