@@ -132,17 +132,26 @@ class MagicalVecEnv:
                                                   int(count)))
         self._draw = (int(first), int(count))
 
-    def refresh_pool(self):
-        """Double-buffered pool streaming: sample fresh scenes into the half of
+    def refresh_pool(self, sampler=None, block=True):
+        """Double-buffered pool streaming: put fresh scenes into the half of
         the pool that is currently NOT drawn from, then make it the draw range.
         Call at most once per episode length (environments still playing the
-        other half finish within one episode).  Returns the new draw range."""
+        other half finish within one episode).  The scenes come from `sampler`
+        (a `pool_sampler.ScenePoolSampler` running ahead in worker processes;
+        with block=False nothing happens and None is returned if it has fewer
+        than half a pool ready) or, without one, are sampled here from the
+        task's RandomState.  Returns the new draw range."""
         half = self.n_scenes // 2
         assert half >= 1, 'refresh_pool needs a pool of at least 2 scenes'
         first, _ = getattr(self, '_draw', (0, self.n_scenes))
         new_first = half if first == 0 else 0
-        self.update_scenes(new_first, [self.task.build_scene()
-                                       for _ in range(half)])
+        if sampler is not None:
+            fresh = sampler.take(half, block=block)
+            if fresh is None:
+                return None
+        else:
+            fresh = [self.task.build_scene() for _ in range(half)]
+        self.update_scenes(new_first, fresh)
         self.set_draw_range(new_first, half)
         return new_first, half
 

@@ -471,3 +471,49 @@ def test_pool_streaming_and_keep_scene(built):
         venv.step(torch.from_numpy(rng.randint(0, 18, size=8).astype(np.int32)).cuda())
     assert [int(venv.get_state(i)['scene']) for i in range(8)] == list(np.arange(8) % 4)
     venv.close()
+
+
+def test_refresh_pool_from_background_sampler(built):
+    """N1 streaming: worker processes sample layouts ahead of the GPU
+    (pool_sampler.ScenePoolSampler); refresh_pool() swaps them into the idle
+    half of the pool every episode, so over three episodes the batch plays
+    three different sets of layouts, each bit-exact against the oracle."""
+    import torch
+    import magical_b200 as magical
+    from magical_b200.pool_sampler import ScenePoolSampler, sample_chunk
+    from oracle_lib import OracleEnv
+    env_id, batch, half = 'MoveToRegion-TestAll-LoRes4E-v0', 48, 6
+    venv = magical.make_vec(env_id, batch, auto_reset=True, n_scenes=2 * half,
+                            seed=4)
+    venv.set_draw_range(0, half)
+    venv.reset(scene_ids=np.arange(batch) % half)
+    rng = np.random.RandomState(1)
+    task, _ = magical.make_task(env_id)
+    expected = np.concatenate([sample_chunk(task, 77, k, 4) for k in range(3)])
+    with ScenePoolSampler(venv.task, workers=2, seed=77, chunk=4) as sampler:
+        for episode in range(2):
+            first, count = venv.refresh_pool(sampler)
+            assert first == (half if episode == 0 else 0) and count == half
+            fresh = venv.scenes[first:first + half]
+            want = expected[episode * half:(episode + 1) * half]
+            assert np.array_equal(np.ascontiguousarray(fresh).view(np.uint8),
+                                  np.ascontiguousarray(want).view(np.uint8))
+            for t in range(venv.max_episode_steps):   # everyone resets once
+                acts = rng.randint(0, 18, size=batch).astype(np.int32)
+                venv.step(torch.from_numpy(acts).cuda())
+            now = [int(venv.get_state(e)['scene']) for e in range(batch)]
+            assert all(first <= s < first + half for s in now), (episode, now)
+            e = 7 + episode
+            orc = OracleEnv(venv.scenes[now[e]], det_sincos=True)
+            for t in range(12):
+                acts = rng.randint(0, 18, size=batch).astype(np.int32)
+                venv.step(torch.from_numpy(acts).cuda())
+                orc.step(int(acts[e]))
+            st, ost = venv.get_state(e), orc.state()
+            nb = int(st['n_bodies'])
+            assert np.array_equal(st['pos'][:nb], ost['pos'][:nb])
+            # finish the episode so that the next swap is safe
+            for t in range(venv.max_episode_steps - 12):
+                acts = rng.randint(0, 18, size=batch).astype(np.int32)
+                venv.step(torch.from_numpy(acts).cuda())
+    venv.close()
