@@ -53,6 +53,7 @@ class MagicalEnv(gymshim.Env):
         self.env_id = env_id
         self._device = device
         self._venv = None
+        self._raw = self._raw_scene = None
         self._randomised = benchmarks.EnvName(env_id).is_test
         self.max_episode_steps = self.spec.max_episode_steps
         self.fps = self.task.fps
@@ -112,12 +113,37 @@ class MagicalEnv(gymshim.Env):
                 {'eval_score': float(info['eval_score'][0].item())})
 
     def render(self, mode='rgb_array'):
+        """Full-resolution views of the current state, as `BaseEnv.render`
+        returns them under every preprocessor (base_env.py:309-338):
+        OrderedDict(allo, ego) of (H, W, 3) u8 frames."""
         if mode != 'rgb_array':
             raise NotImplementedError(
                 "only mode='rgb_array' exists on the GPU path (no window)")
-        return self._host_obs()
+        if self._venv is None:
+            return None
+        if self._mode == sc.OBS_RAW:
+            self._venv.render()
+            return self._host_obs()
+        # preprocessed ids: rasterise the same poses through a raw-mode handle
+        st = self._venv.get_state(0)
+        scene = self._venv.scenes[int(st['scene'])]
+        if self._raw is None or self._raw_scene is not self._venv:
+            if self._raw is not None:
+                self._raw.close()
+            self._raw = MagicalVecEnv(self.task, 1, preproc=None,
+                                      device=self._device, auto_reset=False,
+                                      scenes=[scene])
+            self._raw.reset()
+            self._raw_scene = self._venv
+        for b in range(int(st['n_bodies'])):
+            self._raw.set_pose(0, b, float(st['pos'][b][0]),
+                               float(st['pos'][b][1]), float(st['angle'][b]))
+        obs = self._raw.render().cpu().numpy()
+        return collections.OrderedDict([('allo', obs[0, 0]),
+                                        ('ego', obs[1, 0])])
 
     def close(self):
-        if self._venv is not None:
-            self._venv.close()
-            self._venv = None
+        for v in (self._venv, self._raw):
+            if v is not None:
+                v.close()
+        self._venv = self._raw = self._raw_scene = None
