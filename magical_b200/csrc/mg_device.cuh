@@ -11,7 +11,8 @@
 #include "../../include/magical_b200.h"
 #include "mg_scene_aux.h"
 
-#define MG_NCACHE 24 /* cached contacts: this sub-step's + those of pairs that collided in the last 3 sub-steps */
+#define MG_NCACHE 48 /* cached contacts: this sub-step's (<= 32) + those of pairs that collided in the last 3 sub-steps;
+                        at most 64 (the thread-per-environment kernel tracks matched entries in a 64-bit mask) */
 #define MG_NCON 24   /* solver contacts per sub-step (16 when two environments share a warp) */
 #define MG_NCAND 64  /* narrowphase candidates per sub-step */
 #define MG_PERSISTENCE 3

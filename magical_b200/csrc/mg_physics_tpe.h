@@ -38,7 +38,7 @@
 #include "mg_sincos.h"
 
 #define TPE_CON_WORDS 14
-#define TPE_MAX_CONTACTS 16 /* solver contacts per sub-step (private words first, then the spill area) */
+#define TPE_MAX_CONTACTS 32 /* solver contacts per sub-step (private words first, then the spill area) */
 #define TPE_NO_SLOT 15
 
 #if defined(__CUDACC__)
@@ -197,7 +197,8 @@ MG_HD unsigned long long tpe_unpack_ids(double d) {
 
 
 #if defined(TPE_STATS) && !defined(__CUDACC__)
-extern long tpe_stats[8]; /* host instrumentation: 0 sub-steps, 1 items, 2 items with contacts, 3 box-overlapping group pairs, 4 sep-skipped */
+extern long tpe_stats[8]; /* host instrumentation: 0 sub-steps, 1 items, 2 items with contacts, 3 box-overlapping group pairs, 4 sep-skipped,
+                             5 blocks, 6 blocks walked by the solver */
 #define TPE_STAT(i) (tpe_stats[i]++)
 #else
 #define TPE_STAT(i) ((void)0)
@@ -681,7 +682,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
      * results, in canonical order, with shuffles.  On the host build the "warp" is one lane. */
     ncon = 0;
     bool too_many = false;
-    uint32_t cache_used = 0u;
+    uint64_t cache_used = 0ull;
     const int kcap = T.spill ? TPE_MAX_CONTACTS : T.L.kcon;
     /* turn one pair's manifold into solver contacts of this environment */
     auto take_manifold = [&](int ia, int ib, const Manifold& m) {
@@ -702,7 +703,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
           if (e.stamp == stamp - 1) first = false;
           if (m.hash[0] == e.hash) { jn[0] = e.jn; jt[0] = e.jt; }
           if (m.count > 1 && m.hash[1] == e.hash) { jn[1] = e.jn; jt[1] = e.jt; }
-          cache_used |= 1u << q;
+          cache_used |= 1ull << q;
         }
       }
       const double u = sc.shapes[ia].friction * sc.shapes[ib].friction;
@@ -967,12 +968,14 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     T.V(s_robot, 2) = rw;
 
     /* ---- warm start (cpArbiterApplyCachedImpulse, then the joints' applyCachedImpulse; dt_coef = 1) */
+    uint32_t touched = 0; /* slots that carry a contact in this sub-step */
     for (int c = 0; c < ncon; c++) {
       TpeCon<S> C = tpe_con(T, c);
       const unsigned long long ids = tpe_unpack_ids(C[13]);
-      if ((ids >> 58) & 1ull) continue; /* first contact of the pair */
       const int ba = (int)((ids >> 48) & 0x1F), bb = (int)((ids >> 53) & 0x1F);
       const int sa_ = T.slot(ba), sb_ = T.slot(bb);
+      touched |= (1u << sa_) | (1u << sb_);
+      if ((ids >> 58) & 1ull) continue; /* first contact of the pair */
       const double ma = ba < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[ba].m_inv) : 0.0;
       const double ia_ = ba < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[ba].i_inv) : 0.0;
       const double mb = bb < MG_MAX_BODIES ? TPE_LDG(&sc.bodies[bb].m_inv) : 0.0;
@@ -1012,13 +1015,28 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
       TPE_ANG_WARM(c_lim1, a_lim1, f1w);
       TPE_ANG_WARM(c_mot1, a_mot1, f1w);
     }
+    /* A block that is at rest after the warm start (zero velocity, zero accumulated drag impulses) and
+     * carries no contact stays exactly so through all iterations: its pivot and gear compute j = 0 and
+     * add 0 (only the sign of a zero can differ, which nothing downstream reads).  Each lane therefore
+     * walks only its own moving / touched blocks below, and the warp makes as many trips as its busiest
+     * lane needs instead of one per block. */
+    uint32_t bact = 0;
     for (int k = 0; k < nblk; k++) {
       const int s = ax.tpe_bj_slot[k];
       const TpeJC cp = tpe_jc(ds, ax.tpe_bj_pivot[k]), cg = tpe_jc(ds, ax.tpe_bj_gear[k]);
-      T.V(s, 0) = T.V(s, 0) + T.BJ(k, 0) * cp.mb;
-      T.V(s, 1) = T.V(s, 1) + T.BJ(k, 1) * cp.mb;
-      T.V(s, 2) += T.BJ(k, 2) * cg.ib;
+      const double j0 = T.BJ(k, 0), j1 = T.BJ(k, 1), j2 = T.BJ(k, 2);
+      const double v0 = T.V(s, 0) + j0 * cp.mb, v1 = T.V(s, 1) + j1 * cp.mb;
+      double v2 = T.V(s, 2);
+      v2 += j2 * cg.ib;
+      T.V(s, 0) = v0; T.V(s, 1) = v1; T.V(s, 2) = v2;
+      const bool moving = v0 != 0.0 || v1 != 0.0 || v2 != 0.0 || j0 != 0.0 || j1 != 0.0 || j2 != 0.0 ||
+                          ((touched >> s) & 1u) != 0u;
+      bact |= (moving ? 1u : 0u) << k;
     }
+#if defined(TPE_STATS) && !defined(__CUDACC__)
+    tpe_stats[5] += nblk; /* block joints seen / walked */
+    tpe_stats[6] += __builtin_popcount(bact);
+#endif
     T.V(s_robot, 0) = rvx; T.V(s_robot, 1) = rvy; T.V(s_robot, 2) = rw;
     T.V(s_f0, 0) = f0x; T.V(s_f0, 1) = f0y; T.V(s_f0, 2) = f0w;
     T.V(s_f1, 0) = f1x; T.V(s_f1, 1) = f1y; T.V(s_f1, 2) = f1w;
@@ -1072,9 +1090,12 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
       /* blocks: force-capped pivot + gear against the static body (entities.py:703-711).  Two blocks per
        * trip with all loads issued first: the blocks are independent, and a lone warp per scheduler has
        * nothing but instruction-level parallelism to hide shared-memory and fp64 latency with. */
-      for (int k = 0; k < nblk; k += 2) {
-        const bool two = k + 1 < nblk;
-        const int kb = two ? k + 1 : k;
+      for (uint32_t m = bact; m != 0u;) {
+        const int k = TPE_CTZ(m);
+        m &= m - 1u;
+        const bool two = m != 0u;
+        const int kb = two ? TPE_CTZ(m) : k;
+        m &= m - 1u; /* no-op when m is already empty */
         const int sA = ax.tpe_bj_slot[k], sB = ax.tpe_bj_slot[kb];
         const TpeJC cpA = tpe_jc(ds, ax.tpe_bj_pivot[k]), cgA = tpe_jc(ds, ax.tpe_bj_gear[k]);
         const TpeJC cpB = tpe_jc(ds, ax.tpe_bj_pivot[kb]), cgB = tpe_jc(ds, ax.tpe_bj_gear[kb]);
@@ -1139,7 +1160,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
       int nsurv = 0;
       for (int q = 0; q < n_cache; q++) { /* compact the survivors in place (their rank never exceeds q) */
         const CEntry e = G->cache[q];
-        if (((cache_used >> q) & 1u) == 0 && (stamp - e.stamp) < MG_PERSISTENCE) {
+        if (((cache_used >> q) & 1ull) == 0ull && (stamp - e.stamp) < MG_PERSISTENCE) {
           if (nsurv != q) G->cache[nsurv] = e;
           nsurv++;
         }

@@ -35,7 +35,8 @@ def test_rollouts(built, env_name):
                 action = env.action_space.sample()
                 obs, rew, done, info = env.step(action)
                 traj_len += 1
-                assert rew == 0.0
+                if 'DebugReward' not in env_name:   # base_env.py:290: reward is always 0
+                    assert rew == 0.0
                 assert done or info['eval_score'] == 0.0
             assert traj_len == env.max_episode_steps
             assert 0.0 <= info['eval_score'] <= 1.0
