@@ -248,7 +248,9 @@ int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* sce
  * mg_update_scenes overwrites pool entries [first, first + n) -- the caller must make sure that no environment is
  * still playing them, e.g. by keeping them outside the draw range for at least one episode length;
  * mg_set_draw_range restricts the entries an auto-reset draws from (n = 0: keep each env on its scene).
- * New scenes must fit the capacities the handle reserved at mg_create (largest scene seen then). */
+ * The rasteriser's shared-memory layout grows with the largest scene seen; the physics kernel's layout is fixed
+ * at mg_create, so a new scene with more bodies / shape groups than any scene of the original pool is rejected
+ * (MG_E_INVALID, "exceeds the physics layout", nothing copied). */
 int mg_update_scenes(mg_handle* h, int32_t first, int32_t n, const mg_scene_t* scenes);
 int mg_set_draw_range(mg_handle* h, int32_t first, int32_t n);
 

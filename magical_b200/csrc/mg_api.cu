@@ -504,6 +504,7 @@ int mg_update_scenes(mg_handle* h, int32_t first, int32_t n, const mg_scene_t* s
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const int ss = h->cfg.obs_mode == MG_OBS_RAW ? 1 : 4;
   std::vector<DeviceScene> host(n);
+  int ecap = h->ecap, scap = h->scap, rcap = h->rcap;
   for (int i = 0; i < n; i++) {
     host[i].s = scenes[i];
     const char* why = mg_build_scene_aux(&scenes[i], &host[i].aux);
@@ -511,9 +512,10 @@ int mg_update_scenes(mg_handle* h, int32_t first, int32_t n, const mg_scene_t* s
     int edges = 0, rprims = 0, rows = 0;
     const char* bad = scene_raster_needs(scenes[i], h->res_out * ss, &edges, &rprims, &rows);
     if (bad) return fail(MG_E_INVALID, "mg_update_scenes: %s", bad);
-    /* the kernels' shared-memory layouts were sized at mg_create for the largest scene seen then */
-    if (edges > h->ecap || rows > h->scap || rprims > h->rcap)
-      return fail(MG_E_INVALID, "mg_update_scenes: scene needs more rasteriser capacity than the handle reserved%s", "");
+    /* the rasteriser's shared-memory layout is a launch parameter: it grows with the largest scene seen */
+    if (edges > ecap) ecap = edges;
+    if (rows > scap) scap = rows;
+    if (rprims > rcap) rcap = rprims;
     if (h->use_tpe) {
       const mg_scene_aux_t& ax = host[i].aux;
       const int con_words = h->tpe.scratch_global ? (h->tpe.words - h->tpe.off_con) : (h->tpe.off_it - h->tpe.off_con);
@@ -522,6 +524,15 @@ int mg_update_scenes(mg_handle* h, int32_t first, int32_t n, const mg_scene_t* s
         return fail(MG_E_INVALID, "mg_update_scenes: scene exceeds the physics layout the handle was created with%s", "");
     }
   }
+  ecap = (ecap + 63) / 64 * 64;
+  scap = (scap + 63) / 64 * 64;
+  if (scap < 2 * ecap) scap = 2 * ecap;
+  rcap = (rcap + 31) / 32 * 32;
+  if (mg_raster_smem_bytes(h->cfg.obs_mode, ecap, scap, rcap) > 200 * 1024)
+    return fail(MG_E_INVALID, "mg_update_scenes: scene has too many draw edges for the rasteriser's shared memory%s", "");
+  h->ecap = ecap;
+  h->scap = scap;
+  h->rcap = rcap;
   /* environments bound to these entries must have finished their episodes (caller's contract, see header) */
   CUDA_TRY(cudaMemcpyAsync(h->d_scenes + first, host.data(), sizeof(DeviceScene) * (size_t)n, cudaMemcpyHostToDevice,
                            h->stream));

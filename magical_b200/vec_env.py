@@ -65,6 +65,7 @@ class MagicalVecEnv:
         self.scenes = np.ascontiguousarray(np.stack(scenes)).astype(
             sc.scene_dt, copy=False)
         self.n_scenes = len(self.scenes)
+        self.skipped_scenes = 0
         res = task.res_hw[0]
         cfg = _native.make_config(device=device, batch=self.batch,
                                   n_scenes=self.n_scenes, obs_mode=self.mode,
@@ -122,9 +123,26 @@ class MagicalVecEnv:
         episode length first)."""
         scenes = np.ascontiguousarray(np.stack(scenes)).astype(sc.scene_dt,
                                                                 copy=False)
-        _native.check(self._lib.mg_update_scenes(
-            self._h, int(first), len(scenes), scenes.ctypes.data))
-        self.scenes[first:first + len(scenes)] = scenes
+        try:
+            _native.check(self._lib.mg_update_scenes(
+                self._h, int(first), len(scenes), scenes.ctypes.data))
+            self.scenes[first:first + len(scenes)] = scenes
+            return
+        except _native.NativeError as ex:
+            if 'exceeds the physics layout' not in str(ex):
+                raise
+        # Some scene has more bodies / shape groups than any scene of the pool
+        # the handle was created with (the physics kernel's shared-memory
+        # layout is fixed at mg_create): stream the others, keep the old scene
+        # in those slots, and count them.  Create the handle with a pool large
+        # enough to contain the task's biggest layouts to avoid this.
+        for i in range(len(scenes)):
+            rc = self._lib.mg_update_scenes(self._h, int(first) + i, 1,
+                                            scenes[i:i + 1].ctypes.data)
+            if rc == 0:
+                self.scenes[first + i] = scenes[i]
+            else:
+                self.skipped_scenes += 1
 
     def set_draw_range(self, first, count):
         """Pool entries an auto-reset draws from (count 0: keep the scene)."""
