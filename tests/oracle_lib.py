@@ -171,3 +171,20 @@ def rollout_scores(job):
         pos[e] = st['pos']
         orc.close()
     return score, done_at, pos
+
+
+def rollout_frames(job):
+    """Worker for the render sweep: job = (scene_records, actions[T, n]); steps
+    one oracle per column through its action stream and returns the 96x96
+    allo and ego frames of the final state, [n, 2, 96, 96, 3] u8."""
+    scenes, actions = job
+    n = actions.shape[1]
+    out = np.zeros((n, 2, 96, 96, 3), dtype=np.uint8)
+    for e in range(n):
+        orc = OracleEnv(scenes[e], det_sincos=True)
+        for t in range(actions.shape[0]):
+            orc.step(int(actions[t, e]))
+        out[e, 0] = orc.render_lores(0)
+        out[e, 1] = orc.render_lores(1)
+        orc.close()
+    return out

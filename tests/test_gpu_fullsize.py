@@ -138,3 +138,43 @@ def test_score_sweep_1000_episodes(built, env_id, n_scenes):
     if env_id.startswith('MoveToCorner') or n_scenes:
         assert len(np.unique(score)) > 1, np.unique(score)
     venv.close()
+
+
+@pytest.mark.parametrize('env_id,n_scenes,n_steps', [
+    ('MatchRegions-TestAll-LoResStack-v0', 128, 25),
+    ('ClusterShape-TestAll-LoResStack-v0', 128, 60),
+    ('FindDupe-TestAll-LoResStack-v0', 128, 40),
+    ('MakeLine-TestCountPlus-LoResStack-v0', 128, 50),
+    ('FixColour-TestAll-LoResStack-v0', 128, 15),
+    ('MoveToRegion-TestAll-LoResStack-v0', 128, 33),
+])
+def test_render_sweep_random_layouts(built, env_id, n_scenes, n_steps):
+    """Pixels over many layouts: 512 environments on 128 sampled scenes
+    (random shapes, colours, counts, poses), stepped with random actions;
+    the newest allo and ego frame of EVERY environment equals the oracle's
+    brute-force rasteriser + 4x4 mean, bit for bit."""
+    import multiprocessing as mp
+    import os
+    import torch
+    import magical_b200 as magical
+    from oracle_lib import rollout_frames
+    batch = 512
+    venv = magical.make_vec(env_id, batch, auto_reset=False,
+                            n_scenes=n_scenes, seed=17)
+    scene_ids = np.arange(batch) % n_scenes
+    venv.reset(scene_ids=scene_ids)
+    rng = np.random.RandomState(23)
+    acts = _actions(rng, n_steps, batch, batch)
+    chunk = 16
+    jobs = [([venv.scenes[scene_ids[e]] for e in range(lo, lo + chunk)],
+             acts[:, lo:lo + chunk]) for lo in range(0, batch, chunk)]
+    with mp.get_context('fork').Pool(min(os.cpu_count() or 1, 32)) as pool:
+        want = np.concatenate(pool.map(rollout_frames, jobs))
+    for t in range(n_steps):
+        obs, _, _, _ = venv.step(torch.from_numpy(acts[t]).cuda())
+    got = obs[:, :, :, :, 9:12].cpu().numpy()        # [view, env, 96, 96, 3]
+    for v, name in enumerate(('allo', 'ego')):
+        bad = np.flatnonzero((got[v] != want[:, v]).reshape(batch, -1).any(1))
+        assert len(bad) == 0, (env_id, name, bad[:10],
+                               int((got[v][bad[0]] != want[bad[0], v]).sum()))
+    venv.close()
