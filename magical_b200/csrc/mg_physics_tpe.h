@@ -56,6 +56,14 @@
 #define TPE_CTZ(x) __builtin_ctz(x)
 #endif
 
+/* bits [cell(lo), cell(hi)] of a 16-cell axis over [-1.28, 1.28); cell() is monotone and clamps */
+MG_HD uint32_t tpe_cell_mask(float lo, float hi) {
+  const float a = fminf(fmaxf((lo + 1.28f) * 6.25f, 0.0f), 15.0f);
+  const float b = fminf(fmaxf((hi + 1.28f) * 6.25f, 0.0f), 15.0f);
+  const int ia = (int)a, ib = (int)b; /* truncation of a non-negative value: monotone */
+  return ((2u << ib) - 1u) & ~((1u << ia) - 1u);
+}
+
 MG_HD float tpe_d2f_ru(double x) {
 #if defined(__CUDA_ARCH__)
   return __double2float_ru(x);
@@ -148,6 +156,7 @@ struct Tpe {
   /* group box l, b, r, t (k = 0..3) and, at k = 4, shape0 | nshape << 8 | slot << 16 of the group */
   MG_HDM float& gbb(int g, int k) const { return wf[(L.off_con * 2 + g * 6 + k) * S]; }
   MG_HDM uint32_t& ginfo(int g) const { return reinterpret_cast<uint32_t*>(wf)[(L.off_con * 2 + g * 6 + 4) * S]; }
+  MG_HDM uint32_t& gcell(int g) const { return reinterpret_cast<uint32_t*>(wf)[(L.off_con * 2 + g * 6 + 5) * S]; }
   MG_HDM uint32_t& IT(int k) const { return itp[k * it_st]; }
   MG_HDM uint16_t& SEP(int p) const { return sepp[p * it_st]; }
   /* bind the item / separation-cache views: private words, or `scratch` = this lane's record in HBM */
@@ -621,6 +630,10 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
       T.gbb(g, 0) = l; T.gbb(g, 1) = b; T.gbb(g, 2) = r; T.gbb(g, 3) = t;
       T.ginfo(g) = (uint32_t)sc.cgroups[g].shape0 | ((uint32_t)sc.cgroups[g].nshape << 8) |
                    ((uint32_t)T.slot(gbody) << 16);
+      /* the 16 x 16 grid cells the box touches, as two 16-bit masks (x low, y high): boxes that overlap
+       * share a cell in both axes (the cell index is monotone in the coordinate), so one AND rejects most
+       * of the pair list before any float compare */
+      T.gcell(g) = tpe_cell_mask(l, r) | (tpe_cell_mask(b, t) << 16);
     }
 
     /* ---- broadphase (own environment): canonical pair list -> work items for the exact narrowphase.
@@ -641,8 +654,8 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
         const int p = w0 * 32 + b;
         const unsigned pr = TPE_LDG(reinterpret_cast<const unsigned short*>(&sc.bpairs[p][0]));
         const int ga = (int)(pr & 0xFFu), gb = (int)(pr >> 8);
-        const bool hit = T.gbb(ga, 0) <= T.gbb(gb, 2) && T.gbb(gb, 0) <= T.gbb(ga, 2) &&
-                         T.gbb(ga, 1) <= T.gbb(gb, 3) && T.gbb(gb, 1) <= T.gbb(ga, 3);
+        const uint32_t shared = T.gcell(ga) & T.gcell(gb);
+        const bool hit = (shared & 0xFFFFu) != 0u && (shared >> 16) != 0u;
         m |= (hit ? 1u : 0u) << b;
       }
 #pragma unroll
@@ -658,6 +671,8 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
         bits &= bits - 1u;
         TPE_STAT(3);
         const int ga = sc.bpairs[p][0], gb = sc.bpairs[p][1];
+        if (!(T.gbb(ga, 0) <= T.gbb(gb, 2) && T.gbb(gb, 0) <= T.gbb(ga, 2) &&
+              T.gbb(ga, 1) <= T.gbb(gb, 3) && T.gbb(gb, 1) <= T.gbb(ga, 3))) continue;
         const uint32_t ia_ = T.ginfo(ga), ib_ = T.ginfo(gb);
         const float travelled = tpe_fadd_ru(T.path((int)(ia_ >> 16)), T.path((int)(ib_ >> 16)));
         if (travelled < tpe_sep_get(T, p)) { TPE_STAT(4); continue; }
