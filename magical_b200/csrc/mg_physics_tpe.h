@@ -1102,40 +1102,24 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
         TPE_APPLY(V, sb_, c_mb, c_ib, jx, jy, c_r2x, c_r2y);
         C[9] = c_jn; C[10] = c_jt; C[11] = c_jb;
       }
-      /* blocks: force-capped pivot + gear against the static body (entities.py:703-711).  Two blocks per
-       * trip with all loads issued first: the blocks are independent, and a lone warp per scheduler has
-       * nothing but instruction-level parallelism to hide shared-memory and fp64 latency with. */
-      for (uint32_t m = bact; m != 0u;) {
+      /* blocks: force-capped pivot + gear against the static body (entities.py:703-711); every lane walks
+       * its own live blocks, one per trip (two per trip for instruction-level parallelism measured slower:
+       * the trip count is set by the busiest lane and most lanes have at most one live block) */
+      for (uint32_t m = bact; m != 0u; m &= m - 1u) {
         const int k = TPE_CTZ(m);
-        m &= m - 1u;
-        const bool two = m != 0u;
-        const int kb = two ? TPE_CTZ(m) : k;
-        m &= m - 1u; /* no-op when m is already empty */
-        const int sA = ax.tpe_bj_slot[k], sB = ax.tpe_bj_slot[kb];
+        const int sA = ax.tpe_bj_slot[k];
         const TpeJC cpA = tpe_jc(ds, ax.tpe_bj_pivot[k]), cgA = tpe_jc(ds, ax.tpe_bj_gear[k]);
-        const TpeJC cpB = tpe_jc(ds, ax.tpe_bj_pivot[kb]), cgB = tpe_jc(ds, ax.tpe_bj_gear[kb]);
         double vxA = T.V(sA, 0), vyA = T.V(sA, 1), wA = T.V(sA, 2);
-        double vxB = T.V(sB, 0), vyB = T.V(sB, 1), wB = T.V(sB, 2);
         const double oxA = T.BJ(k, 0), oyA = T.BJ(k, 1), biasA = 0.0;
-        const double oxB = T.BJ(kb, 0), oyB = T.BJ(kb, 1), biasB = 0.0;
-        double gaA = T.BJ(k, 2), gaB = T.BJ(kb, 2);
+        double gaA = T.BJ(k, 2);
         double jxA = (0.0 - (vxA - 0.0)) * cpA.c0, jyA = (0.0 - (vyA - 0.0)) * cpA.c0;
-        double jxB = (0.0 - (vxB - 0.0)) * cpB.c0, jyB = (0.0 - (vyB - 0.0)) * cpB.c0;
         const d2 accA = dvclamp(D2(oxA + jxA, oyA + jyA), cpA.c1);
-        const d2 accB = dvclamp(D2(oxB + jxB, oyB + jyB), cpB.c1);
         jxA = accA.x - oxA; jyA = accA.y - oyA;
-        jxB = accB.x - oxB; jyB = accB.y - oyB;
         vxA = vxA + jxA * cpA.mb; vyA = vyA + jyA * cpA.mb;
-        vxB = vxB + jxB * cpB.mb; vyB = vyB + jyB * cpB.mb;
-        double waA = 0.0, waB = 0.0;
+        double waA = 0.0;
         tpe_gear(cgA, biasA, gaA, waA, wA);
-        tpe_gear(cgB, biasB, gaB, waB, wB);
         T.BJ(k, 0) = accA.x; T.BJ(k, 1) = accA.y; T.BJ(k, 2) = gaA;
         T.V(sA, 0) = vxA; T.V(sA, 1) = vyA; T.V(sA, 2) = wA;
-        if (two) {
-          T.BJ(kb, 0) = accB.x; T.BJ(kb, 1) = accB.y; T.BJ(kb, 2) = gaB;
-          T.V(sB, 0) = vxB; T.V(sB, 1) = vyB; T.V(sB, 2) = wB;
-        }
       }
       /* the robot chain, in insertion order (entities.py:255-354) */
       rvx = T.V(s_robot, 0); rvy = T.V(s_robot, 1); rw = T.V(s_robot, 2);
