@@ -517,3 +517,13 @@ def test_refresh_pool_from_background_sampler(built):
                 acts = rng.randint(0, 18, size=batch).astype(np.int32)
                 venv.step(torch.from_numpy(acts).cuda())
     venv.close()
+
+
+@pytest.mark.parametrize('task_name', ['MatchRegions', 'ClusterShape'])
+def test_fallback_warp_kernel_bit_exact(built, monkeypatch, task_name):
+    """MG_PHYSICS=warp selects the lanes-per-environment kernel (the path for
+    scenes without MAGICAL's canonical structure); it must stay bit-exact
+    against the oracle as well."""
+    monkeypatch.setenv('MG_PHYSICS', 'warp')
+    worst, _ = _rollout_compare(task_name, 60, 33, seed=17)
+    assert worst == 0.0
