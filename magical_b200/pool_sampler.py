@@ -73,16 +73,25 @@ class ScenePoolSampler:
             n += self.chunk
         return n
 
-    def take(self, n, block=True):
+    def take(self, n, block=True, timeout=600.0):
         """The next n scenes of the stream; None if block=False and fewer than
-        n are finished."""
+        n are finished.  A chunk that does not arrive within `timeout` seconds
+        raises RuntimeError (workers that cannot start -- e.g. a parent whose
+        __main__ cannot be re-imported under the spawn start method -- would
+        otherwise block forever)."""
         if not block and self.ready() < n:
             return None
         out = []
         have = 0
         while have < n:
             if self._left is None:
-                self._left = self._pending.popleft().get()
+                try:
+                    self._left = self._pending[0].get(timeout)
+                except mp.TimeoutError:
+                    raise RuntimeError(
+                        'ScenePoolSampler: no scenes from the worker processes '
+                        f'within {timeout:.0f} s') from None
+                self._pending.popleft()
                 self._fill()
             part = self._left[:n - have]
             self._left = self._left[len(part):]
