@@ -10,6 +10,17 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+def _oracle_pool():
+    """Worker processes for the oracle side of the sweeps.  Spawned, not
+    forked: this process holds a CUDA context and its threads, and the
+    workers only need numpy + the oracle's ctypes binding."""
+    import multiprocessing as mp
+    import os
+    import oracle_lib
+    oracle_lib.lib()      # build once here, not concurrently in every worker
+    return mp.get_context('spawn').Pool(min(os.cpu_count() or 1, 32))
+
+
 def _actions(rng, n_steps, batch, n_groups):
     """n_groups distinct action streams, env i follows stream i % n_groups."""
     base = rng.randint(0, 18, size=(n_steps, n_groups)).astype(np.int32)
@@ -109,11 +120,11 @@ def test_score_sweep_1000_episodes(built, env_id, n_scenes):
     n_steps = venv.max_episode_steps
     rng = np.random.RandomState(101)
     acts = _actions(rng, n_steps, batch, batch)
-    # oracle first (forked workers never touch CUDA)
+    # the oracle side runs on all host cores
     chunk = 25
     jobs = [([venv.scenes[scene_ids[e]] for e in range(lo, lo + chunk)],
              acts[:, lo:lo + chunk]) for lo in range(0, batch, chunk)]
-    with mp.get_context('fork').Pool(min(os.cpu_count() or 1, 32)) as pool:
+    with _oracle_pool() as pool:
         res = pool.map(rollout_scores, jobs)
     o_score = np.concatenate([r[0] for r in res])
     o_done = np.concatenate([r[1] for r in res])
@@ -168,7 +179,7 @@ def test_render_sweep_random_layouts(built, env_id, n_scenes, n_steps):
     chunk = 16
     jobs = [([venv.scenes[scene_ids[e]] for e in range(lo, lo + chunk)],
              acts[:, lo:lo + chunk]) for lo in range(0, batch, chunk)]
-    with mp.get_context('fork').Pool(min(os.cpu_count() or 1, 32)) as pool:
+    with _oracle_pool() as pool:
         want = np.concatenate(pool.map(rollout_frames, jobs))
     for t in range(n_steps):
         obs, _, _, _ = venv.step(torch.from_numpy(acts[t]).cuda())
