@@ -89,3 +89,32 @@ class TpeHostEnv:
             self._h = None
 
     __del__ = close
+
+
+def rollout_mismatches(job):
+    """Worker for the host sweep: job = (scene_records, actions[T, n]); steps the
+    host-compiled kernel source and the oracle side by side and returns, per
+    column, None or (step, max |pos difference|, overflow flags) of the first
+    step at which poses differ or the kernel flags an overflow."""
+    from oracle_lib import OracleEnv
+    scenes, actions = job
+    out = []
+    for e in range(actions.shape[1]):
+        orc = OracleEnv(scenes[e], det_sincos=True)
+        env = TpeHostEnv(scenes[e], kcon=4, nitems=48)
+        bad = None
+        for t in range(actions.shape[0]):
+            orc.step(int(actions[t, e]))
+            env.step(int(actions[t, e]))
+            a, b = orc.state(), env.state()
+            nb = int(a['n_bodies'])
+            if int(b['overflow']) or not (
+                    np.array_equal(a['pos'][:nb], b['pos'][:nb])
+                    and np.array_equal(a['angle'][:nb], b['angle'][:nb])):
+                bad = (t, float(np.abs(a['pos'][:nb] - b['pos'][:nb]).max()),
+                       int(b['overflow']))
+                break
+        out.append(bad)
+        orc.close()
+        env.close()
+    return out
