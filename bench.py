@@ -353,12 +353,15 @@ def run_b200(args, env_id, batch):
                            + (' + obs' if args.gather_obs else ''),
             'episode_phase': (f'uniform over the {prelude}-step episode (untimed prelude of {prelude} steps '
                               'with staggered resets)') if prelude > 0 else 'all envs at episode start',
-            'l2': 'state (229 MB) + obs (7.2 GB) per step exceed the 126 MB L2'
+            'l2': 'state (254 MB) + obs (7.2 GB) per step exceed the 126 MB L2'
                   if batch >= 65536 else 'inputs smaller than L2 (small-batch config)',
         },
         'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'ms_per_step': e2e_ms / K,
                 'h2d_bytes_per_step': 4 * batch, 'd2h_bytes_per_step': 9 * batch},
         'gpu_launches': int(launches),
+        # environments x episodes that hit a physics capacity limit on this rank since the handle was created
+        # (prelude + warm-up + all timed loops); anything but 0 would mean results that differ from the reference's
+        'overflow_envs': int(venv.overflow_count()),
         'clocks': clocks.summary(),
         'roofline': roofline,
     }

@@ -279,6 +279,13 @@ int mg_set_pose(mg_handle* h, int32_t env, int32_t body, double x, double y, dou
 int64_t mg_launch_count(const mg_handle* h);
 int mg_synchronize(mg_handle* h);
 
+/* Environments x episodes in which the physics hit a capacity limit since mg_create (more than 32 simultaneous
+ * solver contacts or 48 cached contacts: that sub-step is then solved without contacts / with a truncated cache,
+ * and mg_state_t.overflow of the environment is non-zero until its next reset).  0 on every workload measured;
+ * a caller that needs the reference's behaviour bit for bit checks this after a run.  Synchronises the stream.
+ * (No reference counterpart: Chipmunk's arrays grow.) */
+int mg_overflow_count(mg_handle* h, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     'mg_create', 'mg_destroy', 'mg_bind_obs', 'mg_obs_nbytes', 'mg_reset',
     'mg_step', 'mg_step_physics', 'mg_render', 'mg_score', 'mg_get_state',
     'mg_set_pose', 'mg_launch_count', 'mg_synchronize', 'mg_update_scenes',
-    'mg_set_draw_range',
+    'mg_set_draw_range', 'mg_overflow_count',
 ]
 
 _lib = None
@@ -65,6 +65,7 @@ def load():
     L.mg_synchronize.argtypes = [vp]
     L.mg_update_scenes.argtypes = [vp, i32, i32, vp]
     L.mg_set_draw_range.argtypes = [vp, i32, i32]
+    L.mg_overflow_count.argtypes = [vp, vp]
     if L.mg_version() != sc.ABI_VERSION:
         raise NativeError("ABI version mismatch between Python and library")
     if L.mg_sizeof_scene() != sc.scene_dt.itemsize \

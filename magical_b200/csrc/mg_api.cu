@@ -31,7 +31,7 @@ size_t mg_tpe_smem_bytes(const TpeLayout* L);
 size_t mg_tpe_spill_doubles_per_env(const TpeLayout* L);
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
                              int draw_first, int draw_count, uint32_t reset_seed, float* reward, uint8_t* done,
-                             float* score, cudaStream_t stream);
+                             float* score, unsigned long long* overflow_count, cudaStream_t stream);
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
                             const int32_t* scene_ids, int first_time, cudaStream_t stream);
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
@@ -59,6 +59,7 @@ struct mg_handle {
   TpeLayout tpe;        /* private-word layout of the thread-per-environment kernel */
   double* d_spill;      /* its contact spill area */
   uint32_t* d_scratch;  /* its per-environment work-item / separation-cache records (scratch_global layout) */
+  unsigned long long* d_overflow; /* environments x episodes that hit a physics capacity limit (k_finish counts) */
   /* mg_step software pipeline: the batch is cut into chunks whose physics and raster kernels run on two
    * internal streams, staggered so that the raster of chunk c overlaps the physics of chunk c + 1 (the
    * physics is latency-bound at ~13 % issue utilisation, the raster issue-bound: they share SMs well) */
@@ -251,6 +252,8 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
       (e = cudaMalloc(&h->d_scenes, sizeof(DeviceScene) * (size_t)cfg->n_scenes)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_scene_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_overflow, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(h->d_overflow, 0, sizeof(unsigned long long))) != cudaSuccess ||
       (h->use_tpe && mg_tpe_spill_doubles_per_env(&h->tpe) > 0 &&
        (e = cudaMalloc(&h->d_spill, sizeof(double) * mg_tpe_spill_doubles_per_env(&h->tpe) * ((size_t)cfg->batch + 64))) !=
            cudaSuccess) ||
@@ -315,6 +318,7 @@ int mg_destroy(mg_handle* h) {
   cudaFree(h->d_scene_ids);
   cudaFree(h->d_spill);
   cudaFree(h->d_scratch);
+  cudaFree(h->d_overflow);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   for (int i = 0; i < 2; i++) {
     if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
@@ -379,7 +383,7 @@ static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_de
     CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads,
                                h->stream));
   CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, h->cfg.auto_reset, 0, h->draw_first, h->draw_count,
-                            (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->stream));
+                            (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->d_overflow, h->stream));
   h->launches += 2;
   return MG_OK;
 }
@@ -406,7 +410,7 @@ static int step_pipelined(mg_handle* h, const int32_t* actions_dev, float* rewar
                                    st));
     CUDA_TRY(cudaEventRecord(h->ev_phys[c & 1], st));
     CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, env0, count, h->cfg.auto_reset, 0, h->draw_first, h->draw_count,
-                              (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, st));
+                              (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->d_overflow, st));
     CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, B, h->res_out, h->ecap, h->scap, h->rcap,
                               0, env0, count, st));
     h->launches += 3;
@@ -441,7 +445,7 @@ int mg_render(mg_handle* h) {
 int mg_score(mg_handle* h, float* score_dev) {
   if (!h || !score_dev) return fail(MG_E_INVALID, "mg_score: null argument%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, 0, 1, 0, 1, 0u, nullptr, nullptr, score_dev, h->stream));
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, 0, 1, 0, 1, 0u, nullptr, nullptr, score_dev, nullptr, h->stream));
   h->launches++;
   return MG_OK;
 }
@@ -549,6 +553,16 @@ int mg_set_draw_range(mg_handle* h, int32_t first, int32_t n) {
 }
 
 int64_t mg_launch_count(const mg_handle* h) { return h ? h->launches : 0; }
+
+int mg_overflow_count(mg_handle* h, int64_t* out) {
+  if (!h || !out) return fail(MG_E_INVALID, "mg_overflow_count: null argument%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  unsigned long long v = 0;
+  CUDA_TRY(cudaMemcpyAsync(&v, h->d_overflow, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out = (int64_t)v;
+  return MG_OK;
+}
 
 int mg_synchronize(mg_handle* h) {
   if (!h) return fail(MG_E_INVALID, "mg_synchronize: null handle%s", "");

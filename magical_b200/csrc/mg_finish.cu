@@ -239,7 +239,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) { /* lowbias32 integer has
 __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, int env0, int count,
                          int auto_reset, int mode, int draw_first, int draw_count, uint32_t reset_seed,
                          float* __restrict__ reward,
-                         uint8_t* __restrict__ done, float* __restrict__ score) {
+                         uint8_t* __restrict__ done, float* __restrict__ score,
+                         unsigned long long* __restrict__ overflow_count) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= count) return;
   env += env0; /* this launch covers environments [env0, env0 + count) */
@@ -249,6 +250,12 @@ __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __res
   if (mode == 1) {
     if (score) score[env] = (float)compute_score(st, ds);
     return;
+  }
+  /* capacity overflows of the physics (flags 2 / 4: that sub-step was solved without contacts / the contact
+   * cache was truncated) are counted once per environment and episode, so a caller can check a whole run */
+  if (st.overflow != 0 && (st.overflow & 0x100) == 0) {
+    st.overflow |= 0x100;
+    if (overflow_count) atomicAdd(overflow_count, 1ull);
   }
   int steps = st.episode_steps + 1;
   st.episode_steps = steps;
@@ -299,11 +306,11 @@ __global__ void k_reset(EnvState* __restrict__ states, const DeviceScene* __rest
 
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
                              int draw_first, int draw_count, uint32_t reset_seed, float* reward, uint8_t* done,
-                             float* score, cudaStream_t stream) {
+                             float* score, unsigned long long* overflow_count, cudaStream_t stream) {
   int threads = 128;
   k_finish<<<(count + threads - 1) / threads, threads, 0, stream>>>(states, scenes, env0, count, auto_reset, mode,
                                                                     draw_first, draw_count, reset_seed, reward, done,
-                                                                    score);
+                                                                    score, overflow_count);
   return cudaGetLastError();
 }
 

@@ -228,6 +228,14 @@ class MagicalVecEnv:
     def launch_count(self):
         return int(self._lib.mg_launch_count(self._h))
 
+    def overflow_count(self):
+        """Environments x episodes that hit a physics capacity limit since
+        creation (0 on every measured workload; synchronises the stream)."""
+        import ctypes
+        out = ctypes.c_int64(0)
+        _native.check(self._lib.mg_overflow_count(self._h, ctypes.byref(out)))
+        return int(out.value)
+
     def synchronize(self):
         _native.check(self._lib.mg_synchronize(self._h))
 

@@ -145,6 +145,7 @@ def test_score_sweep_1000_episodes(built, env_id, n_scenes):
         nb = int(st['n_bodies'])
         assert int(st['overflow']) == 0
         assert np.array_equal(st['pos'][:nb], o_pos[e][:nb]), (env_id, e)
+    assert venv.overflow_count() == 0
     # the sweep must exercise the score function, not just zeros
     if env_id.startswith('MoveToCorner') or n_scenes:
         assert len(np.unique(score)) > 1, np.unique(score)

@@ -426,6 +426,8 @@ def test_soak_contact_rich_batch_has_no_overflow(built):
         assert int(st['overflow']) == 0, e
         most = max(most, int(st['n_contacts']))
     assert most >= 4
+    # every environment and episode of the run, not only the sampled ones
+    assert venv.overflow_count() == 0
     venv.close()
 
 
