@@ -31,3 +31,29 @@ def test_contact_rich_episodes_bit_exact_and_no_overflow():
         res = pool.map(tpe_host_lib.rollout_mismatches, jobs)
     bad = [(i, b) for i, b in enumerate(x for r in res for x in r) if b]
     assert not bad, bad[:5]
+
+
+def test_randomised_layouts_bit_exact_and_no_overflow():
+    """The same check over sampled layouts of three randomised variants
+    (64 layouts each, one push-biased episode per layout)."""
+    import oracle_lib
+    import tpe_host_lib
+    oracle_lib.lib()
+    tpe_host_lib.lib()
+    jobs = []
+    for env_id in ('ClusterColour-TestAll-LoRes4E-v0',
+                   'MatchRegions-TestAll-LoRes4E-v0',
+                   'MakeLine-TestCountPlus-LoRes4E-v0'):
+        task, _ = make_task(env_id)
+        task.seed(31)
+        n, n_steps = 64, task.max_episode_steps
+        scenes = [task.build_scene() for _ in range(n)]
+        rng = np.random.RandomState(7)
+        base = rng.randint(0, 18, size=(n_steps, n)).astype(np.int32)
+        push = rng.choice([1, 4, 7, 10, 13, 16], size=(n_steps, n))
+        acts = np.where(rng.rand(n_steps, n) < 0.5, base, push).astype(np.int32)
+        jobs += [(scenes[lo:lo + 8], acts[:, lo:lo + 8]) for lo in range(0, n, 8)]
+    with mp.get_context('spawn').Pool(min(os.cpu_count() or 1, 16)) as pool:
+        res = pool.map(tpe_host_lib.rollout_mismatches, jobs)
+    bad = [(i, b) for i, b in enumerate(x for r in res for x in r) if b]
+    assert not bad, bad[:5]
