@@ -61,7 +61,16 @@ class ShardedVecEnv:
       obs:    the LOCAL observation shard (or the gathered global batch when
               gather_obs=True),
       reward/done/score: always gathered to the global batch.
+
+    gather_obs='newest' (channel-last stacked layouts LoRes4E / LoRes4A only)
+    all-gathers just the newest frame of every env (27 648 B instead of
+    110 592 B per env and step) and rebuilds the 4-frame stacks of the global
+    batch on each rank: shift by one frame, append the gathered frame, and
+    refill the stack of every env that auto-reset in this step with its first
+    frame, as `FlattenFrameStack.reset` does (benchmarks/__init__.py:130-136).
     """
+
+    FRAME_C, DEPTH = 3, 4
 
     def __init__(self, make_local_env, total, rank, world, gather_obs=False,
                  group=None):
@@ -75,12 +84,33 @@ class ShardedVecEnv:
 
     def reset(self):
         obs = self.local.reset()
-        return self._maybe_gather_obs(obs)
+        out = self._maybe_gather_obs(obs)
+        if self.gather_obs == 'newest' and self.world > 1:
+            self._global = out.clone()      # full gather once per reset
+            return self._global
+        return out
 
     def _maybe_gather_obs(self, obs):
         if not self.gather_obs or self.world == 1:
             return obs
         return all_gather_shards(obs, self.sizes, self.group)
+
+    def _gather_newest(self, obs, done_global):
+        """Global stacks from the newest frames only (see the class docstring)."""
+        c, depth = self.FRAME_C, self.DEPTH
+        assert obs.shape[-1] == c * depth, \
+            "gather_obs='newest' needs a channel-last 4-frame stack"
+        newest = all_gather_shards(obs[..., c * (depth - 1):].contiguous(),
+                                   self.sizes, self.group)
+        g = self._global
+        g[..., :c * (depth - 1)] = g[..., c:].clone()
+        g[..., c * (depth - 1):] = newest
+        if getattr(self.local, 'auto_reset', False):
+            fresh = done_global.bool()
+            if bool(fresh.any()):
+                g[fresh] = newest[fresh].repeat(
+                    *([1] * (newest.dim() - 1)), depth)
+        return g
 
     def step(self, global_actions):
         local_actions = global_actions[self.start:self.stop]
@@ -91,6 +121,8 @@ class ShardedVecEnv:
                 self.group)
             rew, done, score = unpack_scalars(packed)
             info = {'eval_score': score}
+            if self.gather_obs == 'newest':
+                return self._gather_newest(obs, done), rew, done, info
         return self._maybe_gather_obs(obs), rew, done, info
 
     def close(self):
