@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 1
+#define MG_ABI_VERSION 2
 
 /* capacity limits of one compiled scene */
 #define MG_MAX_BODIES 16   /* non-static bodies (<=15 dynamic + 1 kinematic) */
@@ -197,7 +197,8 @@ typedef struct {
   int32_t res;          /* MG_OBS_RAW: render resolution (384); ignored otherwise */
   int32_t auto_reset;   /* 1: envs that finish an episode are reset inside mg_step
                               and the returned observation is the new episode's first */
-  int32_t fast_math;    /* 0: fp64, contraction off (parity build); 1: fp64 with FMA */
+  int32_t reserved0_;   /* must be 0 (was `fast_math`: the library has ONE arithmetic, fp64 with contraction off,
+                           the reference's -- a faster, narrower solver would not be the reference's path) */
   int32_t reset_seed;   /* n_scenes > 1 with auto_reset: an env that finishes an episode draws its next
                            scene on the device as hash(reset_seed, env, resets so far) % n_scenes (the
                            reference re-randomises the layout on every reset, base_env.py:177-234) */
@@ -206,17 +207,33 @@ typedef struct {
   int32_t reserved_[7];
 } mg_config_t;
 
-/* One environment's simulator state in host-readable form (parity tests). */
+/* One environment's COMPLETE simulator state in host-readable form: what mg_get_state returns and
+ * mg_set_state restores (checkpoint / resume, parity tests).  Everything Chipmunk carries from one
+ * cpSpaceStep to the next is here: poses, velocities, the pending bias velocities, the joints'
+ * accumulated impulses and the arbiter cache (one entry per cached contact: shape pair, contact
+ * hash, age of the pair's last collision in sub-steps, accumulated impulses). */
+#define MG_STATE_CACHE 48
 typedef struct {
   int32_t n_bodies, n_joints, n_contacts, episode_steps;
-  int32_t scene, overflow, pad_[2];
+  int32_t scene, overflow;
+  int32_t n_cache;  /* valid entries of cache_* */
+  int32_t stamp;    /* sub-steps simulated since the episode's reset */
   double pos[MG_MAX_BODIES][2];
   double angle[MG_MAX_BODIES];
   double vel[MG_MAX_BODIES][2];
   double angvel[MG_MAX_BODIES];
   double joint_acc[MG_MAX_JOINTS][2]; /* accumulated impulses (jAcc / jnAcc) */
+  /* contacts of the last sub-step (a view of the cache entries with age 0; ignored by mg_set_state) */
   int32_t contact_shapes[32][2];
   double contact_jn[32], contact_jt[32];
+  /* pending bias velocities (cpBody v_bias / w_bias: consumed by the next position update) */
+  double bias_vel[MG_MAX_BODIES][2];
+  double bias_angvel[MG_MAX_BODIES];
+  /* arbiter cache (Chipmunk keeps a pair's contacts for collision_persistence = 3 steps) */
+  int32_t cache_shapes[MG_STATE_CACHE][2]; /* type-ordered shape indices */
+  uint32_t cache_hash[MG_STATE_CACHE];     /* contact feature id */
+  int32_t cache_age[MG_STATE_CACHE];       /* stamp - stamp of the pair's last collision: 0, 1 or 2 */
+  double cache_jn[MG_STATE_CACHE], cache_jt[MG_STATE_CACHE];
 } mg_state_t;
 
 typedef struct mg_handle mg_handle;
@@ -236,6 +253,26 @@ int mg_destroy(mg_handle* h);
 /* Bind the caller-owned DEVICE observation buffer (layout per cfg->obs_mode). */
 int mg_bind_obs(mg_handle* h, void* obs_dev, int64_t nbytes);
 int64_t mg_obs_nbytes(const mg_handle* h);
+/* Two-plane layouts (LoResStack, RAW) with the planes `plane_stride` bytes apart instead of back to back, so a
+ * rank's shard can be rendered straight into its slice of a larger [2, B_global, ...] tensor (multi-GPU, 8(e)). */
+int mg_bind_obs_planes(mg_handle* h, void* plane0_dev, int64_t plane_nbytes, int64_t plane_stride);
+
+/* Optional second output of the render: every environment's NEWEST frame alone, u8 [views, B, 96, 96, 3]
+ * (views = 2 for LoResStack: allo then ego; LoRes4E / LoRes4A: 1).  It is the send buffer of the multi-GPU
+ * observation all-gather: 27 648 B per environment and view instead of the 110 592 B stack.
+ * NULL unbinds.  mg_newest_nbytes is 0 for layouts without this output (3EA, CHW4E, RAW). */
+int64_t mg_newest_nbytes(const mg_handle* h);
+int mg_bind_newest(mg_handle* h, void* newest_dev, int64_t nbytes);
+
+/* FlattenFrameStack for environments rendered elsewhere (benchmarks/__init__.py:118-136): for every env in
+ * [env_first, env_first + env_count) of `stacks_dev` (u8 [n, res, res, 12]) drop the oldest frame and append
+ * the env's frame from `newest_dev`; where fresh_dev[env] != 0 (the env auto-reset in this step) all four
+ * slots are filled with it.  The frame of env e is read at
+ *   newest_dev + (e / shard) * newest_rank_stride + (e % shard) * res * res * 3
+ * (the layout an all-gather of per-rank [views, shard, res, res, 3] buffers produces).  Handle-free: runs on
+ * the current device on `cuda_stream`. */
+int mg_stack_push(void* stacks_dev, const void* newest_dev, const uint8_t* fresh_dev, int64_t env_first,
+                  int64_t env_count, int32_t shard, int64_t newest_rank_stride, int32_t res, void* cuda_stream);
 
 /* Reset environments: BaseEnv.reset (base_env.py:177-234) + FlattenFrameStack.reset
  * (benchmarks/__init__.py:130-136).  env_ids: HOST int32[n] (NULL => all); scene_ids: HOST
@@ -264,7 +301,12 @@ int mg_step(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t
 /* Physics only (no render): used by parity tests and the physics-only bench leg. */
 int mg_step_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev,
                     uint8_t* done_dev, float* score_dev);
-/* Render + stack only, from the current state. */
+/* The render half of mg_step (mg_step == mg_step_physics + mg_step_render): rasterise the current state and
+ * PUSH the frame onto the stacks.  Call exactly once per mg_step_physics. */
+int mg_step_render(mg_handle* h);
+/* Re-render the current state WITHOUT advancing the stacks: the newest frame is replaced in place (raw layout:
+ * the frame is redrawn), so calling it any number of times leaves the next observation unchanged, like the
+ * reference's env.render() (base_env.py:309-338). */
 int mg_render(mg_handle* h);
 
 /* Evaluate each env's end-of-trajectory score for its CURRENT state
@@ -273,6 +315,13 @@ int mg_score(mg_handle* h, float* score_dev);
 
 /* Host-readable snapshot / overwrite of one environment (synchronises the stream). */
 int mg_get_state(mg_handle* h, int32_t env, mg_state_t* out);
+/* Restore one environment from a snapshot taken with mg_get_state (of this or another handle running the
+ * same scene): poses, velocities, bias velocities, joint accumulators, arbiter cache, episode step counter.
+ * The environment keeps its scene binding; `in->n_bodies` / `in->n_joints` must match the scene (MG_E_INVALID
+ * otherwise).  Rotations are re-derived from the angles with the library's sincos, so get -> set -> step
+ * continues bit for bit.  The observation stack is not touched (call mg_render for a frame of the new state).
+ * SURVEY 8(b) `mg_set_state`; no reference counterpart (pymunk spaces are pickled whole). */
+int mg_set_state(mg_handle* h, int32_t env, const mg_state_t* in);
 int mg_set_pose(mg_handle* h, int32_t env, int32_t body, double x, double y, double angle);
 
 /* Number of kernels launched by this handle since creation (bench bookkeeping). */

@@ -18,8 +18,9 @@ ABI_SYMBOLS = [
     'mg_version', 'mg_last_error', 'mg_sizeof_scene', 'mg_sizeof_state',
     'mg_create', 'mg_destroy', 'mg_bind_obs', 'mg_obs_nbytes', 'mg_reset',
     'mg_step', 'mg_step_physics', 'mg_render', 'mg_score', 'mg_get_state',
-    'mg_set_pose', 'mg_launch_count', 'mg_synchronize', 'mg_update_scenes',
-    'mg_set_draw_range', 'mg_overflow_count',
+    'mg_set_state', 'mg_set_pose', 'mg_launch_count', 'mg_synchronize', 'mg_update_scenes',
+    'mg_set_draw_range', 'mg_overflow_count', 'mg_bind_obs_planes',
+    'mg_newest_nbytes', 'mg_bind_newest', 'mg_stack_push', 'mg_step_render',
 ]
 
 _lib = None
@@ -57,8 +58,15 @@ def load():
     L.mg_step.argtypes = [vp, vp, vp, vp, vp]
     L.mg_step_physics.argtypes = [vp, vp, vp, vp, vp]
     L.mg_render.argtypes = [vp]
+    L.mg_step_render.argtypes = [vp]
+    L.mg_bind_obs_planes.argtypes = [vp, vp, i64, i64]
+    L.mg_newest_nbytes.restype = i64
+    L.mg_newest_nbytes.argtypes = [vp]
+    L.mg_bind_newest.argtypes = [vp, vp, i64]
+    L.mg_stack_push.argtypes = [vp, vp, vp, i64, i64, i32, i64, i32, vp]
     L.mg_score.argtypes = [vp, vp]
     L.mg_get_state.argtypes = [vp, i32, vp]
+    L.mg_set_state.argtypes = [vp, i32, vp]
     L.mg_set_pose.argtypes = [vp, i32, i32, f64, f64, f64]
     L.mg_launch_count.restype = i64
     L.mg_launch_count.argtypes = [vp]

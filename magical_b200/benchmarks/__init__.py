@@ -198,9 +198,26 @@ _TASKS = [
 ]
 
 
+def _gym_module():
+    """The real `gym` package when it is importable (it is not part of the
+    build image; the reference pins gym==0.17.*), else None."""
+    try:
+        import gym
+        return gym if hasattr(gym, 'register') else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def _register(env_id, entry_point, preproc, ep_len, kwargs):
     ALL_REGISTERED_ENVS.append(env_id)
     ENV_SPECS[env_id] = EnvSpec(env_id, entry_point, preproc, ep_len, kwargs)
+    # the upper surface is kept verbatim (reference benchmarks/__init__.py:976-999):
+    # with gym present, `gym.make(env_id)` builds the GPU-backed env, wrapped in
+    # gym's own TimeLimit by `max_episode_steps` exactly like the reference's ids
+    gym = _gym_module()
+    if gym is not None:
+        gym.register(env_id, entry_point='magical_b200.env:MagicalEnv',
+                     max_episode_steps=ep_len, kwargs={'env_id': env_id})
 
 
 def register_envs():

@@ -21,6 +21,7 @@
 #include "mg_device.cuh"
 #include "mg_physics_tpe.h"
 #include "mg_sincos.h"
+#include "mg_state_io.h"
 
 cudaError_t mg_launch_physics(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
                               int lanes_per_env, int block_threads, cudaStream_t stream);
@@ -34,9 +35,11 @@ cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int en
                              float* score, unsigned long long* overflow_count, cudaStream_t stream);
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
                             const int32_t* scene_ids, int first_time, cudaStream_t stream);
-cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
-                             int res_out, int ecap, int scap, int rcap, int only_fresh, int env0, int count,
-                             cudaStream_t stream);
+cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, uint8_t* newest,
+                             size_t plane_stride, int batch, int res_out, int ecap, int scap, int rcap, int only_fresh,
+                             int push, int env0, int count, cudaStream_t stream);
+cudaError_t mg_launch_stack_push(uint8_t* stacks, const uint8_t* newest, const uint8_t* fresh, long long env_first,
+                                 long long env_count, int shard, long long rank_stride, int res, cudaStream_t stream);
 cudaError_t mg_raster_upload_units(const double* units);
 size_t mg_raster_smem_bytes(int mode, int ecap, int scap, int rcap);
 
@@ -49,6 +52,8 @@ struct mg_handle {
   int32_t* d_scene_ids;
   uint8_t* obs;
   int64_t obs_bytes;
+  int64_t plane_stride; /* bytes between the two view planes of obs (LoResStack / RAW) */
+  uint8_t* newest;      /* optional second output: every environment's newest frame (mg_bind_newest) */
   int res_out;
   int ecap;
   int scap;             /* span-table rows the rasteriser reserves per view */
@@ -334,15 +339,62 @@ int mg_bind_obs(mg_handle* h, void* obs_dev, int64_t nbytes) {
   if (nbytes != h->obs_bytes) return fail(MG_E_INVALID, "mg_bind_obs: buffer size does not match the observation layout%s", "");
   if (((uintptr_t)obs_dev & 15) != 0) return fail(MG_E_INVALID, "mg_bind_obs: buffer must be 16-byte aligned%s", "");
   h->obs = (uint8_t*)obs_dev;
+  h->plane_stride = nbytes / 2; /* only read by the two-plane layouts */
+  return MG_OK;
+}
+
+int mg_bind_obs_planes(mg_handle* h, void* plane0_dev, int64_t plane_nbytes, int64_t plane_stride) {
+  if (!h || !plane0_dev) return fail(MG_E_INVALID, "mg_bind_obs_planes: null argument%s", "");
+  if (h->cfg.obs_mode != MG_OBS_LORESSTACK && h->cfg.obs_mode != MG_OBS_RAW)
+    return fail(MG_E_INVALID, "mg_bind_obs_planes: the observation layout has a single plane (use mg_bind_obs)%s", "");
+  if (plane_nbytes * 2 != h->obs_bytes) return fail(MG_E_INVALID, "mg_bind_obs_planes: plane size does not match the layout%s", "");
+  if (plane_stride < plane_nbytes || (plane_stride & 15) != 0 || ((uintptr_t)plane0_dev & 15) != 0)
+    return fail(MG_E_INVALID, "mg_bind_obs_planes: planes must not overlap and must be 16-byte aligned%s", "");
+  h->obs = (uint8_t*)plane0_dev;
+  h->plane_stride = plane_stride;
+  return MG_OK;
+}
+
+int64_t mg_newest_nbytes(const mg_handle* h) {
+  if (!h) return -1;
+  switch (h->cfg.obs_mode) {
+    case MG_OBS_LORES4E:
+    case MG_OBS_LORES4A: return (int64_t)h->cfg.batch * h->res_out * h->res_out * 3;
+    case MG_OBS_LORESSTACK: return 2 * (int64_t)h->cfg.batch * h->res_out * h->res_out * 3;
+  }
+  return 0; /* layout has no newest-frame output */
+}
+
+int mg_bind_newest(mg_handle* h, void* newest_dev, int64_t nbytes) {
+  if (!h) return fail(MG_E_INVALID, "mg_bind_newest: null handle%s", "");
+  if (!newest_dev) { h->newest = nullptr; return MG_OK; }
+  if (mg_newest_nbytes(h) <= 0)
+    return fail(MG_E_INVALID, "mg_bind_newest: only the LoRes4E / LoRes4A / LoResStack layouts have a newest-frame output%s", "");
+  if (nbytes != mg_newest_nbytes(h)) return fail(MG_E_INVALID, "mg_bind_newest: buffer size does not match%s", "");
+  if (((uintptr_t)newest_dev & 3) != 0) return fail(MG_E_INVALID, "mg_bind_newest: buffer must be 4-byte aligned%s", "");
+  h->newest = (uint8_t*)newest_dev;
+  return MG_OK;
+}
+
+int mg_stack_push(void* stacks_dev, const void* newest_dev, const uint8_t* fresh_dev, int64_t env_first,
+                  int64_t env_count, int32_t shard, int64_t newest_rank_stride, int32_t res, void* cuda_stream) {
+  if (!stacks_dev || !newest_dev) return fail(MG_E_INVALID, "mg_stack_push: null argument%s", "");
+  if (env_first < 0 || env_count < 0 || shard <= 0 || res <= 0 || res % 4 != 0 || newest_rank_stride < 0)
+    return fail(MG_E_INVALID, "mg_stack_push: bad range%s", "");
+  if (((uintptr_t)stacks_dev & 15) != 0 || ((uintptr_t)newest_dev & 3) != 0 || (newest_rank_stride & 3) != 0)
+    return fail(MG_E_INVALID, "mg_stack_push: stacks must be 16-byte and frames 4-byte aligned%s", "");
+  CUDA_TRY(mg_launch_stack_push((uint8_t*)stacks_dev, (const uint8_t*)newest_dev, fresh_dev, env_first, env_count, shard,
+                                newest_rank_stride, res, (cudaStream_t)cuda_stream));
   return MG_OK;
 }
 
 int64_t mg_obs_nbytes(const mg_handle* h) { return h ? h->obs_bytes : -1; }
 
-static int do_raster(mg_handle* h, int only_fresh) {
+static int do_raster(mg_handle* h, int only_fresh, int push) {
   if (!h->obs) return fail(MG_E_STATE, "no observation buffer bound (call mg_bind_obs first)%s", "");
-  CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->cfg.batch, h->res_out, h->ecap,
-                            h->scap, h->rcap, only_fresh, 0, h->cfg.batch, h->stream));
+  CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->newest, (size_t)h->plane_stride,
+                            h->cfg.batch, h->res_out, h->ecap, h->scap, h->rcap, only_fresh, push, 0, h->cfg.batch,
+                            h->stream));
   h->launches++;
   return MG_OK;
 }
@@ -369,7 +421,7 @@ int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* sce
   h->launches++;
   /* the host arrays may be reused by the caller as soon as we return */
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (h->obs) return do_raster(h, 1);
+  if (h->obs) return do_raster(h, 1, 1);
   return MG_OK;
 }
 
@@ -411,8 +463,8 @@ static int step_pipelined(mg_handle* h, const int32_t* actions_dev, float* rewar
     CUDA_TRY(cudaEventRecord(h->ev_phys[c & 1], st));
     CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, env0, count, h->cfg.auto_reset, 0, h->draw_first, h->draw_count,
                               (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->d_overflow, st));
-    CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, B, h->res_out, h->ecap, h->scap, h->rcap,
-                              0, env0, count, st));
+    CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->newest, (size_t)h->plane_stride, B,
+                              h->res_out, h->ecap, h->scap, h->rcap, 0, 1, env0, count, st));
     h->launches += 3;
   }
   for (int i = 0; i < 2; i++) {
@@ -428,7 +480,7 @@ int mg_step(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t
   if (h->n_chunks > 1) return step_pipelined(h, actions_dev, reward_dev, done_dev, score_dev);
   int rc = do_physics(h, actions_dev, reward_dev, done_dev, score_dev);
   if (rc != MG_OK) return rc;
-  return do_raster(h, 0);
+  return do_raster(h, 0, 1);
 }
 
 int mg_step_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
@@ -436,10 +488,16 @@ int mg_step_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev,
   return do_physics(h, actions_dev, reward_dev, done_dev, score_dev);
 }
 
+int mg_step_render(mg_handle* h) {
+  if (!h) return fail(MG_E_INVALID, "mg_step_render: null handle%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  return do_raster(h, 0, 1);
+}
+
 int mg_render(mg_handle* h) {
   if (!h) return fail(MG_E_INVALID, "mg_render: null handle%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  return do_raster(h, 0);
+  return do_raster(h, 0, 0);
 }
 
 int mg_score(mg_handle* h, float* score_dev) {
@@ -461,28 +519,25 @@ int mg_get_state(mg_handle* h, int32_t env, mg_state_t* out) {
   if (!ds) return fail(MG_E_NOMEM, "mg_get_state: out of host memory%s", "");
   cudaError_t e = cudaMemcpy(ds, h->d_scenes + st.scene, sizeof(DeviceScene), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { free(ds); return fail(MG_E_CUDA, "mg_get_state: %s", cudaGetErrorString(e)); }
-  memset(out, 0, sizeof(*out));
-  out->n_bodies = ds->s.n_bodies;
-  out->n_joints = ds->s.n_joints;
-  out->episode_steps = st.episode_steps;
-  out->scene = st.scene;
-  out->overflow = st.overflow;
-  for (int b = 0; b < ds->s.n_bodies; b++) {
-    out->pos[b][0] = st.P[b].x; out->pos[b][1] = st.P[b].y; out->angle[b] = st.P[b].z;
-    out->vel[b][0] = st.V[b].x; out->vel[b][1] = st.V[b].y; out->angvel[b] = st.V[b].z;
-  }
-  for (int j = 0; j < ds->s.n_joints; j++) { out->joint_acc[j][0] = st.jacc[j].x; out->joint_acc[j][1] = st.jacc[j].y; }
-  int nc = 0;
-  for (int k = 0; k < st.n_cache && k < MG_NCACHE && nc < 32; k++) {
-    if (st.cache[k].stamp != st.stamp) continue; /* only contacts of the last sub-step */
-    out->contact_shapes[nc][0] = st.cache[k].a;
-    out->contact_shapes[nc][1] = st.cache[k].b;
-    out->contact_jn[nc] = st.cache[k].jn;
-    out->contact_jt[nc] = st.cache[k].jt;
-    nc++;
-  }
-  out->n_contacts = nc;
+  mg_state_export(st, ds->s, out);
   free(ds);
+  return MG_OK;
+}
+
+int mg_set_state(mg_handle* h, int32_t env, const mg_state_t* in) {
+  if (!h || !in) return fail(MG_E_INVALID, "mg_set_state: null argument%s", "");
+  if (env < 0 || env >= h->cfg.batch) return fail(MG_E_INVALID, "mg_set_state: env out of range%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  EnvState st;
+  CUDA_TRY(cudaMemcpyAsync(&st, h->d_states + env, sizeof(EnvState), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  /* the snapshot must describe the scene this environment is bound to (header counts only are fetched) */
+  int32_t hdr[16];
+  CUDA_TRY(cudaMemcpy(hdr, &h->d_scenes[st.scene].s, sizeof(hdr), cudaMemcpyDeviceToHost));
+  const mg_scene_t* sc = reinterpret_cast<const mg_scene_t*>(hdr);
+  const char* why = mg_state_import(st, sc->n_bodies, sc->n_joints, sc->n_shapes, in);
+  if (why) return fail(MG_E_INVALID, "mg_set_state: %s", why);
+  CUDA_TRY(cudaMemcpy(h->d_states + env, &st, sizeof(EnvState), cudaMemcpyHostToDevice));
   return MG_OK;
 }
 

@@ -748,7 +748,11 @@ size_t mg_physics_smem_bytes(int lanes_per_env, int threads) { return sizeof(Env
 template <int G, int THREADS>
 static cudaError_t launch_g(EnvState* states, const DeviceScene* scenes, const int32_t* actions, int batch,
                             cudaStream_t stream) {
-  static bool configured = false;
+  static bool configured_on[64] = {false}; /* per device: the attribute does not carry over to other GPUs */
+  int dev = 0;
+  cudaError_t de = cudaGetDevice(&dev);
+  if (de != cudaSuccess) return de;
+  bool& configured = configured_on[dev & 63];
   size_t smem = mg_physics_smem_bytes(G, THREADS);
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_physics<G, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -47,7 +47,12 @@ cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, c
                                   int count, const TpeLayout* L, double* spill, uint32_t* scratch,
                                   cudaStream_t stream) {
   const size_t smem = mg_tpe_smem_bytes(L);
-  static size_t configured = 0;
+  /* the opt-in is a per-DEVICE function attribute: one process may hold handles on several GPUs */
+  static size_t configured_on[64] = {0};
+  int dev = 0;
+  cudaError_t de = cudaGetDevice(&dev);
+  if (de != cudaSuccess) return de;
+  size_t& configured = configured_on[dev & 63];
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(k_physics_tpe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

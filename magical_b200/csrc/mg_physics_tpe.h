@@ -558,6 +558,9 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
   for (int sub = 0; sub < MG_SUBSTEPS; ++sub) {
     stamp++;
     TPE_STAT(0);
+    /* warp fence: the previous sub-step's cooperative stages read other lanes' pose words, and the group boxes
+     * written below share their words with other lanes' solver contacts of the previous sub-step */
+    tpe_sync<S>();
     /* ---- Robot.update (entities.py:459-479) */
     double rate0, rate1;
     {
@@ -742,6 +745,9 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
     };
     {
       const int lane = tpe_lane<S>();
+      /* warp fence: every lane's poses and work items are written, and nobody reads a group box any more
+       * (contacts born below reuse those words), before lanes start working on each other's environments */
+      tpe_sync<S>();
       /* ---- stage A: exact boxes of every item, one item per lane.  A pair whose boxes are disjoint is
        * settled here: the gap is a lower bound of the shapes' distance and goes into the item's level. */
       {
@@ -833,6 +839,7 @@ MG_HD void tpe_env_step(Tpe<S> T, EnvState* __restrict__ G, const DeviceScene* _
           }
         }
       }
+      tpe_sync<S>();
       /* survivors beyond the packed list (rare): by the owner itself, still in canonical order */
       if (n_surv > TPE_MAX_SURV) {
         const int last_coop = (int)((surv >> (6 * (TPE_MAX_SURV - 1))) & 63u);

@@ -652,17 +652,20 @@ __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int t
   }
 }
 
-/* shift one pixel's 12 stack bytes left by one frame and append colour n (or replicate when fresh) */
-__device__ __forceinline__ void stack_push(uint32_t* w, uint32_t n, bool fresh) {
+/* shift one pixel's 12 stack bytes left by one frame and append colour n (or replicate when fresh);
+ * push == false (mg_render of an unchanged step): only the newest frame's 3 bytes are replaced */
+__device__ __forceinline__ void stack_push(uint32_t* w, uint32_t n, bool fresh, bool push = true) {
   if (fresh) {
     w[0] = n | (n << 24);
     w[1] = (n >> 8) | (n << 16);
     w[2] = (n >> 16) | (n << 8);
-  } else {
+  } else if (push) {
     uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
     w[0] = (w0 >> 24) | (w1 << 8);
     w[1] = (w1 >> 24) | (w2 << 8);
     w[2] = (w2 >> 24) | (n << 8);
+  } else {
+    w[2] = (w[2] & 0xFFu) | (n << 8);
   }
 }
 
@@ -670,8 +673,9 @@ __device__ __forceinline__ void stack_push(uint32_t* w, uint32_t n, bool fresh) 
  * MODE: MG_OBS_*;  SS: samples per output pixel side (4 for the LoRes modes, 1 for RAW). */
 template <int MODE>
 __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_BLOCKS)
-k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, uint8_t* __restrict__ obs, int batch,
-         int res_out, int ecap, int scap, int rcap, int only_fresh, int env0) {
+k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, uint8_t* __restrict__ obs,
+         uint8_t* __restrict__ newest, size_t plane_stride /* bytes between the two view planes of obs */, int batch,
+         int res_out, int ecap, int scap, int rcap, int only_fresh, int push, int env0) {
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
   /* LoResStack and RAW keep their two views in separate planes, so the views are rendered one after the
    * other through the same shared memory (NPASS = 2, one resident view): half the footprint, twice the CTAs
@@ -767,9 +771,9 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           !fresh) {
 #pragma unroll
         for (int v = 0; v < 1; v++) {
-          size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * batch : 0;
+          const size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * plane_stride : 0;
           const uint4* ptr =
-              reinterpret_cast<const uint4*>(obs + ((plane + env) * frame_px + (size_t)Y * res_out + X0) * 12);
+              reinterpret_cast<const uint4*>(obs + plane + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
           /* streaming accesses: every byte of the stack is touched exactly once per step */
           pre[v][0] = __ldcs(ptr); pre[v][1] = __ldcs(ptr + 1); pre[v][2] = __ldcs(ptr + 2);
         }
@@ -789,8 +793,8 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
         /* [B, R, R, 12] (LoResStack: [2, B, R, R, 12]): 4 pixels = 48 bytes = 3 x uint4 */
 #pragma unroll
         for (int v = 0; v < 1; v++) {
-          size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * batch : 0;
-          uint4* ptr = reinterpret_cast<uint4*>(obs + ((plane + env) * frame_px + (size_t)Y * res_out + X0) * 12);
+          const size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * plane_stride : 0;
+          uint4* ptr = reinterpret_cast<uint4*>(obs + plane + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
           uint32_t w[12];
           if (!fresh) {
             uint4 a = pre[v][0], b = pre[v][1], c = pre[v][2];
@@ -798,10 +802,20 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
             w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
           }
 #pragma unroll
-          for (int i = 0; i < 4; i++) stack_push(&w[3 * i], col[v][i], fresh);
+          for (int i = 0; i < 4; i++) stack_push(&w[3 * i], col[v][i], fresh, push != 0);
           __stcs(ptr, make_uint4(w[0], w[1], w[2], w[3]));
           __stcs(ptr + 1, make_uint4(w[4], w[5], w[6], w[7]));
           __stcs(ptr + 2, make_uint4(w[8], w[9], w[10], w[11]));
+          if (newest) {
+            /* newest frame alone, [views][batch][R][R][3]: the send buffer of the multi-GPU observation
+             * gather (27 648 B per environment instead of the 110 592 B stack) */
+            uint32_t* np_ = reinterpret_cast<uint32_t*>(
+                newest + (((MODE == MG_OBS_LORESSTACK ? (size_t)pass * batch : 0) + env) * frame_px + (size_t)Y * res_out + X0) * 3);
+            const uint32_t c0 = col[v][0], c1 = col[v][1], c2 = col[v][2], c3 = col[v][3];
+            __stcs(np_, c0 | (c1 << 24));
+            __stcs(np_ + 1, (c1 >> 8) | (c2 << 16));
+            __stcs(np_ + 2, (c2 >> 16) | (c3 << 8));
+          }
         }
       } else if (MODE == MG_OBS_LORES3EA) {
         /* bytes 0..2 = newest allo frame; bytes 3..11 = 3 ego frames, oldest first */
@@ -819,6 +833,9 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
             w[3 * i] = al | (eg << 24);
             w[3 * i + 1] = (eg >> 8) | (eg << 16);
             w[3 * i + 2] = (eg >> 16) | (eg << 8);
+          } else if (!push) {
+            w[3 * i] = al | (w[3 * i] & 0xFF000000u);
+            w[3 * i + 2] = (w[3 * i + 2] & 0xFFu) | (eg << 8);
           } else {
             uint32_t w1 = w[3 * i + 1], w2 = w[3 * i + 2];
             uint32_t b6 = (w1 >> 16) & 0xFF, b7 = (w1 >> 24) & 0xFF;
@@ -842,6 +859,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           uint32_t* p2 = reinterpret_cast<uint32_t*>(base + (size_t)(6 + c) * frame_px);
           uint32_t* p3 = reinterpret_cast<uint32_t*>(base + (size_t)(9 + c) * frame_px);
           if (fresh) { *p0 = nw; *p1 = nw; *p2 = nw; *p3 = nw; }
+          else if (!push) { *p3 = nw; }
           else { uint32_t a = *p1, b = *p2, d = *p3; *p0 = a; *p1 = b; *p2 = d; *p3 = nw; }
         }
       } else {
@@ -849,7 +867,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
 #pragma unroll
         for (int v = 0; v < 1; v++) {
           uint32_t* ptr = reinterpret_cast<uint32_t*>(
-              obs + (((size_t)pass * batch + env) * frame_px + (size_t)Y * res_out + X0) * 3);
+              obs + (size_t)pass * plane_stride + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 3);
           uint32_t c0 = col[v][0], c1 = col[v][1], c2 = col[v][2], c3 = col[v][3];
           ptr[0] = c0 | (c1 << 24);
           ptr[1] = (c1 >> 8) | (c2 << 16);
@@ -880,28 +898,34 @@ cudaError_t mg_raster_upload_units(const double* units /* [130][2] */) {
 }
 
 template <int MODE>
-static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch, int res_out,
-                               int ecap, int scap, int rcap, int only_fresh, int env0, int count,
-                               cudaStream_t stream) {
+static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint8_t* obs, uint8_t* newest,
+                               size_t plane_stride, int batch, int res_out, int ecap, int scap, int rcap,
+                               int only_fresh, int push, int env0, int count, cudaStream_t stream) {
   size_t smem = mg_raster_smem_bytes(MODE, ecap, scap, rcap);
   cudaError_t e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  k_raster<MODE><<<count, RASTER_THREADS, smem, stream>>>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0);
+  k_raster<MODE><<<count, RASTER_THREADS, smem, stream>>>(states, scenes, obs, newest, plane_stride, batch, res_out, ecap,
+                                                          scap, rcap, only_fresh, push, env0);
   return cudaGetLastError();
 }
 
-cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, int batch,
-                             int res_out, int ecap, int scap, int rcap, int only_fresh, int env0, int count,
-                             cudaStream_t stream) {
+cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, uint8_t* newest,
+                             size_t plane_stride, int batch, int res_out, int ecap, int scap, int rcap, int only_fresh,
+                             int push, int env0, int count, cudaStream_t stream) {
+#define MG_RASTER_CASE(M)                                                                                            \
+  case M:                                                                                                            \
+    return launch_mode<M>(states, scenes, obs, newest, plane_stride, batch, res_out, ecap, scap, rcap, only_fresh, push, \
+                          env0, count, stream);
   switch (mode) {
-    case MG_OBS_LORES4E: return launch_mode<MG_OBS_LORES4E>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
-    case MG_OBS_LORES4A: return launch_mode<MG_OBS_LORES4A>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
-    case MG_OBS_LORES3EA: return launch_mode<MG_OBS_LORES3EA>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
-    case MG_OBS_LORESSTACK: return launch_mode<MG_OBS_LORESSTACK>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
-    case MG_OBS_LORESCHW4E: return launch_mode<MG_OBS_LORESCHW4E>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
-    case MG_OBS_RAW: return launch_mode<MG_OBS_RAW>(states, scenes, obs, batch, res_out, ecap, scap, rcap, only_fresh, env0, count, stream);
+    MG_RASTER_CASE(MG_OBS_LORES4E)
+    MG_RASTER_CASE(MG_OBS_LORES4A)
+    MG_RASTER_CASE(MG_OBS_LORES3EA)
+    MG_RASTER_CASE(MG_OBS_LORESSTACK)
+    MG_RASTER_CASE(MG_OBS_LORESCHW4E)
+    MG_RASTER_CASE(MG_OBS_RAW)
   }
+#undef MG_RASTER_CASE
   return cudaErrorInvalidValue;
 }

@@ -31,15 +31,19 @@ def make_task(env_id):
 
 
 def make_vec(env_id, batch, device=0, auto_reset=True, n_scenes=None,
-             seed=None, stream=None):
+             seed=None, stream=None, alloc_obs=True, keep_scene=False):
     """Batched GPU env for a registered id.  Demo variants share one scene;
-    randomised Test variants pre-sample `n_scenes` scenes (default 64)."""
+    randomised Test variants pre-sample `n_scenes` scenes (default 64).
+    alloc_obs=False leaves the observation buffer to the caller (`bind_obs`,
+    e.g. a slice of a multi-GPU global batch); keep_scene=True restarts every
+    env on the scene it is bound to instead of redrawing from the pool."""
     task, spec = make_task(env_id)
     if n_scenes is None:
         n_scenes = 64 if benchmarks.EnvName(env_id).is_test else 1
     return MagicalVecEnv(task, batch, preproc=spec.preproc, device=device,
                          auto_reset=auto_reset, n_scenes=n_scenes, seed=seed,
-                         stream=stream)
+                         stream=stream, alloc_obs=alloc_obs,
+                         keep_scene=keep_scene)
 
 
 def make(env_id, device=0):

@@ -8,8 +8,9 @@ copied to the GPU (and handed to the CPU oracle in tests).
 """
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_BODIES = 16
+STATE_CACHE = 48
 MAX_SHAPES = 72
 MAX_CVERTS = 384
 MAX_JOINTS = 32
@@ -80,18 +81,22 @@ scene_dt = np.dtype([
 
 config_dt = np.dtype([('device', 'i4'), ('batch', 'i4'), ('n_scenes', 'i4'),
                       ('obs_mode', 'i4'), ('res', 'i4'), ('auto_reset', 'i4'),
-                      ('fast_math', 'i4'), ('reset_seed', 'i4'),
+                      ('reserved0_', 'i4'), ('reset_seed', 'i4'),
                       ('keep_scene', 'i4'), ('reserved_', 'i4', 7)], align=True)
 
 state_dt = np.dtype([
     ('n_bodies', 'i4'), ('n_joints', 'i4'), ('n_contacts', 'i4'),
     ('episode_steps', 'i4'), ('scene', 'i4'), ('overflow', 'i4'),
-    ('pad_', 'i4', 2),
+    ('n_cache', 'i4'), ('stamp', 'i4'),
     ('pos', 'f8', (MAX_BODIES, 2)), ('angle', 'f8', MAX_BODIES),
     ('vel', 'f8', (MAX_BODIES, 2)), ('angvel', 'f8', MAX_BODIES),
     ('joint_acc', 'f8', (MAX_JOINTS, 2)),
     ('contact_shapes', 'i4', (32, 2)),
     ('contact_jn', 'f8', 32), ('contact_jt', 'f8', 32),
+    ('bias_vel', 'f8', (MAX_BODIES, 2)), ('bias_angvel', 'f8', MAX_BODIES),
+    ('cache_shapes', 'i4', (STATE_CACHE, 2)), ('cache_hash', 'u4', STATE_CACHE),
+    ('cache_age', 'i4', STATE_CACHE),
+    ('cache_jn', 'f8', STATE_CACHE), ('cache_jt', 'f8', STATE_CACHE),
 ], align=True)
 
 

@@ -66,11 +66,16 @@ class MagicalVecEnv:
             sc.scene_dt, copy=False)
         self.n_scenes = len(self.scenes)
         self.skipped_scenes = 0
+        # pool entries resets draw from, and the env-step at which that range
+        # last changed (refresh_pool's safety interlock)
+        self._draw = (0, 0 if keep_scene else self.n_scenes)
+        self._steps = 0
+        self._draw_changed_at = 0
+        self._all_in_range = False  # every env known to play a draw-range entry
         res = task.res_hw[0]
         cfg = _native.make_config(device=device, batch=self.batch,
                                   n_scenes=self.n_scenes, obs_mode=self.mode,
                                   res=res, auto_reset=int(self.auto_reset),
-                                  fast_math=0,
                                   reset_seed=int(self.rng.randint(1 << 31)),
                                   keep_scene=int(bool(keep_scene)))
         import ctypes
@@ -82,8 +87,10 @@ class MagicalVecEnv:
                 cfg.ctypes.data, self.scenes.ctypes.data,
                 ctypes.c_void_p(self._stream.cuda_stream),
                 ctypes.byref(self._h)))
-            # alloc_obs=False: physics-only use (step_physics / eval_score);
-            # step() and render() then fail with "no observation buffer bound"
+            # alloc_obs=False: physics-only use (step_physics / eval_score), or
+            # the caller binds its own buffer with bind_obs(); until then
+            # step() and render() fail with "no observation buffer bound"
+            self.obs_shape = obs_shape(self.mode, self.batch, res)
             self.obs = torch.zeros(obs_shape(self.mode, self.batch, res),
                                    dtype=torch.uint8, device=self.device) \
                 if alloc_obs else None
@@ -107,13 +114,20 @@ class MagicalVecEnv:
             env_ids = np.ascontiguousarray(env_ids, dtype=np.int32)
             n = len(env_ids)
             ids_p = env_ids.ctypes.data
-        if scene_ids is None and self.n_scenes > 1:
-            scene_ids = self.rng.randint(0, self.n_scenes, size=n)
+        if scene_ids is None and self.n_scenes > 1 and self._draw[1] > 0:
+            # host-side draws respect the draw range, like the device-side
+            # redraw of an auto-reset does
+            first, count = self._draw
+            scene_ids = first + self.rng.randint(0, count, size=n)
         if scene_ids is not None:
             scene_ids = np.ascontiguousarray(scene_ids, dtype=np.int32)
             assert len(scene_ids) == n
             sid_p = scene_ids.ctypes.data
         _native.check(self._lib.mg_reset(self._h, ids_p, n, sid_p))
+        if env_ids is None and scene_ids is not None and self._draw[1] > 0:
+            first, count = self._draw
+            self._all_in_range = bool(((scene_ids >= first)
+                                       & (scene_ids < first + count)).all())
         return self.obs
 
     # -- scene pool maintenance (randomised variants) ----------------------
@@ -148,20 +162,38 @@ class MagicalVecEnv:
         """Pool entries an auto-reset draws from (count 0: keep the scene)."""
         _native.check(self._lib.mg_set_draw_range(self._h, int(first),
                                                   int(count)))
+        if (int(first), int(count)) != self._draw:
+            self._draw_changed_at = self._steps
+            self._all_in_range = False
         self._draw = (int(first), int(count))
 
     def refresh_pool(self, sampler=None, block=True):
         """Double-buffered pool streaming: put fresh scenes into the half of
         the pool that is currently NOT drawn from, then make it the draw range.
-        Call at most once per episode length (environments still playing the
-        other half finish within one episode).  The scenes come from `sampler`
+        The first call only narrows the draw range to the first half (no
+        entry can be overwritten while environments may be playing it); later
+        calls return None without doing anything until one episode length of
+        steps has passed since the last switch (environments still playing
+        the other half finish within one episode).  The scenes come from `sampler`
         (a `pool_sampler.ScenePoolSampler` running ahead in worker processes;
         with block=False nothing happens and None is returned if it has fewer
         than half a pool ready) or, without one, are sampled here from the
         task's RandomState.  Returns the new draw range."""
         half = self.n_scenes // 2
         assert half >= 1, 'refresh_pool needs a pool of at least 2 scenes'
-        first, _ = getattr(self, '_draw', (0, self.n_scenes))
+        first, count = self._draw
+        if count != half or first not in (0, half):
+            # First call (or a custom range): environments may be playing any
+            # entry, so nothing can be overwritten yet.  Only narrow the draw
+            # range to the first half; the other half drains within one episode
+            # and is replaced by the next call.
+            self.set_draw_range(0, half)
+            return 0, half
+        if not self._all_in_range and \
+                self._steps - self._draw_changed_at < self.max_episode_steps:
+            # environments bound to the idle half before the last switch may
+            # still be mid-episode on it (mg_update_scenes' contract)
+            return None
         new_first = half if first == 0 else 0
         if sampler is not None:
             fresh = sampler.take(half, block=block)
@@ -182,6 +214,7 @@ class MagicalVecEnv:
         _native.check(self._lib.mg_step(
             self._h, actions.data_ptr(), self.reward.data_ptr(),
             self.done.data_ptr(), self.score.data_ptr()))
+        self._steps += 1
         return self.obs, self.reward, self.done, {'eval_score': self.score}
 
     def step_physics(self, actions):
@@ -190,11 +223,72 @@ class MagicalVecEnv:
         _native.check(self._lib.mg_step_physics(
             self._h, actions.data_ptr(), self.reward.data_ptr(),
             self.done.data_ptr(), self.score.data_ptr()))
+        self._steps += 1
         return self.reward, self.done, {'eval_score': self.score}
 
+    def step_render(self):
+        """The render half of `step()`: pairs 1:1 with `step_physics()`
+        (step == step_physics + step_render); pushes a frame onto the stacks."""
+        _native.check(self._lib.mg_step_render(self._h))
+        return self.obs
+
     def render(self):
+        """Redraw the current state without advancing the frame stacks (the
+        newest frame is replaced in place): idempotent, like the reference's
+        `env.render()` (base_env.py:309-338)."""
         _native.check(self._lib.mg_render(self._h))
         return self.obs
+
+    # -- output buffers owned by the caller (multi-GPU sharding) -----------
+    def bind_obs(self, obs):
+        """Render into `obs` from now on: a contiguous CUDA uint8 tensor of
+        this handle's layout, e.g. this rank's slice of a global observation
+        tensor.  For the two-plane layouts (LoResStack, raw) `obs` may also be
+        a [2, B, ...] view whose planes are contiguous but apart."""
+        assert obs.dtype == self._torch.uint8 and obs.device == self.device
+        shape = obs_shape(self.mode, self.batch, self.task.res_hw[0])
+        assert tuple(obs.shape) == shape, (tuple(obs.shape), shape)
+        if obs.is_contiguous():
+            _native.check(self._lib.mg_bind_obs(self._h, obs.data_ptr(),
+                                                obs.numel()))
+        else:
+            assert len(shape) == 5 and obs[0].is_contiguous() \
+                and obs[1].is_contiguous(), 'planes must be contiguous'
+            _native.check(self._lib.mg_bind_obs_planes(
+                self._h, obs[0].data_ptr(), obs[0].numel(),
+                obs[1].data_ptr() - obs[0].data_ptr()))
+        self.obs = obs
+        return obs
+
+    def newest_shape(self):
+        """Shape of the optional newest-frame output, or None when the layout
+        has none (only LoRes4E / LoRes4A / LoResStack)."""
+        n = int(self._lib.mg_newest_nbytes(self._h))
+        if n <= 0:
+            return None
+        return (n // (self.batch * 96 * 96 * 3), self.batch, 96, 96, 3)
+
+    def bind_newest(self, newest):
+        """Also write every environment's newest frame alone into `newest`
+        (u8 [views, B, 96, 96, 3], CUDA, contiguous; None unbinds): the send
+        buffer of the multi-GPU observation gather."""
+        if newest is None:
+            _native.check(self._lib.mg_bind_newest(self._h, None, 0))
+        else:
+            assert newest.is_contiguous() and newest.device == self.device
+            _native.check(self._lib.mg_bind_newest(self._h, newest.data_ptr(),
+                                                   newest.numel()))
+        self._newest = newest
+
+    def bind_scalars(self, reward, done, score):
+        """Let step() write reward f32[B] / done u8[B] / eval_score f32[B] into
+        caller-owned CUDA tensors (e.g. views of one packed send buffer)."""
+        torch = self._torch
+        for t, dt in ((reward, torch.float32), (done, torch.uint8),
+                      (score, torch.float32)):
+            assert t.dtype == dt and t.shape == (self.batch,) \
+                and t.is_contiguous() and t.device == self.device
+        self.reward, self.done, self.score = reward, done, score
 
     def eval_score(self):
         """score_on_end_of_traj of every env's current state."""
@@ -220,6 +314,14 @@ class MagicalVecEnv:
         _native.check(self._lib.mg_get_state(self._h, int(env),
                                              st.ctypes.data))
         return st
+
+    def set_state(self, env, state):
+        """Restore one environment from a `get_state` snapshot (poses,
+        velocities, bias velocities, joint accumulators, contact cache,
+        episode step): checkpoint / resume of the simulator state."""
+        st = np.ascontiguousarray(state, dtype=sc.state_dt)
+        _native.check(self._lib.mg_set_state(self._h, int(env),
+                                             st.ctypes.data))
 
     def set_pose(self, env, body, x, y, angle):
         _native.check(self._lib.mg_set_pose(self._h, int(env), int(body),

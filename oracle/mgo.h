@@ -100,6 +100,7 @@ void mgo_space_step(mgo_env* e, double dt);
 void mgo_phys_steps_on_frame(mgo_env* e);
 void mgo_step(mgo_env* e, int action, float* reward, uint8_t* done, float* score);
 void mgo_get_state(const mgo_env* e, mg_state_t* out);
+void mgo_set_state(mgo_env* e, const mg_state_t* in);
 void mgo_set_pose(mgo_env* e, int body, double x, double y, double angle);
 void mgo_collide(const mgo_env* e, int ia, int ib, int* out_a, int* out_b, v2* n, int* count, v2 p1[2], v2 p2[2],
                  unsigned hash[2]);

@@ -985,4 +985,65 @@ void mgo_get_state(const mgo_env* e, mg_state_t* out) {
     }
   }
   out->n_contacts = nc;
+  /* the complete carry-over state (mg_state_t v2): bias velocities and the arbiter cache, this sub-step's
+   * arbiters first (collision order), then the older ones */
+  out->stamp = e->stamp;
+  for (int i = 0; i < e->n_bodies; i++) {
+    out->bias_vel[i][0] = e->bodies[i].v_bias.x; out->bias_vel[i][1] = e->bodies[i].v_bias.y;
+    out->bias_angvel[i] = e->bodies[i].w_bias;
+  }
+  int ne = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int n = pass == 0 ? e->n_active : e->n_cached;
+    for (int i = 0; i < n; i++) {
+      const mgo_arbiter* arb = &e->cached[pass == 0 ? e->active[i] : i];
+      if (pass == 1 && arb->stamp == e->stamp) continue; /* already listed */
+      for (int k = 0; k < arb->count && ne < MG_STATE_CACHE; k++, ne++) {
+        out->cache_shapes[ne][0] = arb->a; out->cache_shapes[ne][1] = arb->b;
+        out->cache_hash[ne] = arb->contacts[k].hash;
+        out->cache_age[ne] = e->stamp - arb->stamp;
+        out->cache_jn[ne] = arb->contacts[k].jnAcc; out->cache_jt[ne] = arb->contacts[k].jtAcc;
+      }
+    }
+  }
+  out->n_cache = ne;
+}
+
+/* restore a snapshot (mg_set_state's counterpart): entries of one shape pair form one arbiter; an arbiter that
+ * collided in the last sub-step (age 0) is NORMAL, older ones are CACHED (what cpSpaceStep leaves behind) */
+void mgo_set_state(mgo_env* e, const mg_state_t* in) {
+  for (int i = 0; i < e->n_bodies; i++) {
+    mgo_body* b = &e->bodies[i];
+    b->p = V(in->pos[i][0], in->pos[i][1]);
+    b->a = in->angle[i];
+    rot_for_angle(e, b->a, &b->rot);
+    b->v = V(in->vel[i][0], in->vel[i][1]);
+    b->w = in->angvel[i];
+    b->v_bias = V(in->bias_vel[i][0], in->bias_vel[i][1]);
+    b->w_bias = in->bias_angvel[i];
+  }
+  for (int i = 0; i < e->n_shapes; i++) if (e->shapes[i].body >= 0) shape_cache(e, &e->shapes[i]);
+  for (int i = 0; i < e->n_joints; i++) e->joints[i].jAcc = V(in->joint_acc[i][0], in->joint_acc[i][1]);
+  e->stamp = in->stamp;
+  /* cpSpace.curr_dt: the warm start scales cached impulses by dt / prev_dt (0 before the first step) */
+  e->curr_dt = in->stamp > 0 ? DT : 0.0;
+  e->episode_steps = in->episode_steps;
+  e->overflow = in->overflow;
+  e->n_cached = 0;
+  e->n_active = 0;
+  for (int k = 0; k < in->n_cache; k++) {
+    mgo_arbiter* arb = arbiter_find(e, in->cache_shapes[k][0], in->cache_shapes[k][1], 1);
+    if (!arb || arb->count >= 2) continue;
+    mgo_contact* con = &arb->contacts[arb->count++];
+    memset(con, 0, sizeof(*con));
+    con->hash = in->cache_hash[k];
+    con->jnAcc = in->cache_jn[k]; con->jtAcc = in->cache_jt[k];
+    arb->stamp = in->stamp - in->cache_age[k];
+    arb->state = in->cache_age[k] == 0 ? MGO_ARB_NORMAL : MGO_ARB_CACHED;
+    arb->body_a = e->shapes[arb->a].body;
+    arb->body_b = e->shapes[arb->b].body;
+    /* arbiters of the last sub-step are the active list (collision order = snapshot order) */
+    if (in->cache_age[k] == 0 && arb->count == 1 && e->n_active < MGO_MAX_ARBITERS)
+      e->active[e->n_active++] = (int)(arb - e->cached);
+  }
 }

@@ -12,6 +12,8 @@ for p in (ROOT, os.path.join(ROOT, 'tests')):
 def pytest_configure(config):
     config.addinivalue_line(
         'markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    config.addinivalue_line(
+        'markers', 'allow_overflow: the test provokes a physics capacity overflow on purpose')
 
 
 @pytest.fixture(scope='session')
@@ -47,3 +49,28 @@ def make_demo_task(name, **extra):
     kw = dict(DEMO_KW, max_episode_steps=ep_len)
     kw.update(extra)
     return cls(**kw)
+
+
+@pytest.fixture(autouse=True)
+def _no_physics_overflow(request, monkeypatch):
+    """Bit-exactness claims must fail loudly when the physics hits a capacity
+    limit: every `MagicalVecEnv` a GPU test closes is
+    checked for `overflow_count() == 0` first.  Tests that provoke an
+    overflow on purpose carry `@pytest.mark.allow_overflow`."""
+    if request.node.get_closest_marker('gpu') is None \
+            or request.node.get_closest_marker('allow_overflow') is not None:
+        yield
+        return
+    from magical_b200 import vec_env
+    seen = []
+    orig_close = vec_env.MagicalVecEnv.close
+
+    def checked_close(self):
+        if getattr(self, '_h', None):
+            seen.append(self.overflow_count())
+        orig_close(self)
+
+    monkeypatch.setattr(vec_env.MagicalVecEnv, 'close', checked_close)
+    yield
+    assert all(v == 0 for v in seen), \
+        f'physics capacity overflow in {sum(1 for v in seen if v)} handle(s): {seen}'

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../magical_b200/csrc/mg_physics_tpe.h"
+#include "../../magical_b200/csrc/mg_state_io.h"
 
 struct TpeHostEnv {
   DeviceScene ds;
@@ -77,30 +78,9 @@ void tpeh_set_pose(TpeHostEnv* e, int body, double x, double y, double angle) {
 }
 
 // same conversion as mg_get_state (mg_api.cu)
-void tpeh_get_state(const TpeHostEnv* e, mg_state_t* out) {
-  const EnvState& st = e->st;
-  const mg_scene_t& sc = e->ds.s;
-  memset(out, 0, sizeof(*out));
-  out->n_bodies = sc.n_bodies;
-  out->n_joints = sc.n_joints;
-  out->episode_steps = st.episode_steps;
-  out->scene = st.scene;
-  out->overflow = st.overflow;
-  for (int b = 0; b < sc.n_bodies; b++) {
-    out->pos[b][0] = st.P[b].x; out->pos[b][1] = st.P[b].y; out->angle[b] = st.P[b].z;
-    out->vel[b][0] = st.V[b].x; out->vel[b][1] = st.V[b].y; out->angvel[b] = st.V[b].z;
-  }
-  for (int j = 0; j < sc.n_joints; j++) { out->joint_acc[j][0] = st.jacc[j].x; out->joint_acc[j][1] = st.jacc[j].y; }
-  int nc = 0;
-  for (int k = 0; k < st.n_cache && k < MG_NCACHE && nc < 32; k++) {
-    if (st.cache[k].stamp != st.stamp) continue;
-    out->contact_shapes[nc][0] = st.cache[k].a;
-    out->contact_shapes[nc][1] = st.cache[k].b;
-    out->contact_jn[nc] = st.cache[k].jn;
-    out->contact_jt[nc] = st.cache[k].jt;
-    nc++;
-  }
-  out->n_contacts = nc;
+void tpeh_get_state(const TpeHostEnv* e, mg_state_t* out) { mg_state_export(e->st, e->ds.s, out); }
+int tpeh_set_state(TpeHostEnv* e, const mg_state_t* in) {
+  return mg_state_import(e->st, e->ds.s.n_bodies, e->ds.s.n_joints, e->ds.s.n_shapes, in) ? -1 : 0;
 }
 
 }  // extern "C"

@@ -44,6 +44,7 @@ def lib():
         L.mgo_phys_steps_on_frame.argtypes = [vp]
         L.mgo_step.argtypes = [vp, i32, vp, vp, vp]
         L.mgo_get_state.argtypes = [vp, vp]
+        L.mgo_set_state.argtypes = [vp, vp]
         L.mgo_set_pose.argtypes = [vp, i32, f64, f64, f64]
         L.mgo_score.restype = f64
         L.mgo_score.argtypes = [vp]
@@ -104,6 +105,10 @@ class OracleEnv:
         st = np.zeros((), dtype=sc.state_dt)
         self._lib.mgo_get_state(self._h, st.ctypes.data)
         return st
+
+    def set_state(self, st):
+        st = np.ascontiguousarray(st, dtype=sc.state_dt)
+        self._lib.mgo_set_state(self._h, st.ctypes.data)
 
     def set_pose(self, body, x, y, angle):
         self._lib.mgo_set_pose(self._h, body, x, y, angle)

@@ -105,25 +105,35 @@ def test_two_rank_gloo_equals_single_process(tmp_path, total):
 
 class FakeStackEnv:
     """A stand-in with the real observation contract: channel-last stack of 4
-    RGB frames, oldest first, refilled with the first frame of the new episode
-    when an env auto-resets (the step's obs is then that refilled stack)."""
+    RGB frames per view, oldest first, refilled with the first frame of the
+    new episode when an env auto-resets (the step's obs is then that refilled
+    stack).  views=2 mimics LoResStack's [2, n, H, W, 12] layout."""
     auto_reset = True
+    device = 'cpu'
+    H = W = 2
 
-    def __init__(self, start, n):
+    def __init__(self, start, n, views=1):
         import torch
         self.idx = torch.arange(start, start + n)
         self.t = 0
         self.stack = None
+        self.views = views
+        self.preproc = 'LoResStack' if views == 2 else 'LoRes4E'
+        self.obs_shape = (n, 2, 2, 12) if views == 1 else (2, n, 2, 2, 12)
 
     def _frame(self, salt):
         import torch
-        v = (self.idx * 7 + salt).to(torch.uint8)                      # [n]
         px = torch.arange(2 * 2 * 3, dtype=torch.uint8).view(1, 2, 2, 3)
-        return v.view(-1, 1, 1, 1) + px                                 # [n, 2, 2, 3]
+        fr = [(self.idx * 7 + salt + 101 * v).to(torch.uint8).view(-1, 1, 1, 1) + px
+              for v in range(self.views)]
+        return fr[0] if self.views == 1 else torch.stack(fr)           # [(2,) n, 2, 2, 3]
+
+    def _rep(self, frame):
+        return frame.repeat(*([1] * (frame.dim() - 1)), 4)
 
     def reset(self):
         self.t = 0
-        self.stack = self._frame(0).repeat(1, 1, 1, 4)
+        self.stack = self._rep(self._frame(0))
         return self.stack.clone()
 
     def step(self, actions):
@@ -132,9 +142,9 @@ class FakeStackEnv:
         new = self._frame(self.t * 13) + actions.to(torch.uint8).view(-1, 1, 1, 1)
         self.stack = torch.cat([self.stack[..., 3:], new], dim=-1)
         done = ((self.idx + self.t) % 5 == 0)
-        first = self._frame(self.t * 31 + 5)
-        self.stack[done] = first[done].repeat(1, 1, 1, 4)
-        rew = torch.zeros(len(self.idx))
+        first = self._rep(self._frame(self.t * 31 + 5))
+        self.stack[..., done, :, :, :] = first[..., done, :, :, :]
+        rew = self.idx.float() * 0.25 + self.t
         score = done.float() * 0.5
         return self.stack.clone(), rew, done.to(torch.uint8), {'eval_score': score}
 
@@ -142,8 +152,24 @@ class FakeStackEnv:
         pass
 
 
-def _worker_newest(rank, world, port, total, out):
+def ref_stack_push(stacks, newest, fresh, env_first, env_count, shard, rank_stride):
+    """Plain-torch statement of what `mg_stack_push` must do (host-logic tests
+    only; the product path calls the CUDA kernel and has no CPU form)."""
+    import torch
+    H, W = stacks.shape[1:3]
+    fb = H * W * 3
+    for e in range(env_first, env_first + env_count):
+        off = (e // shard) * rank_stride + (e % shard) * fb
+        frame = newest[off:off + fb].view(H, W, 3)
+        if fresh is not None and int(fresh[e]):
+            stacks[e] = frame.repeat(1, 1, 4)
+        else:
+            stacks[e] = torch.cat([stacks[e][..., 3:], frame], dim=-1)
+
+
+def _worker_newest(rank, world, port, total, views, out):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import torch
     import torch.distributed as dist
     from magical_b200 import dist as mdist
@@ -151,35 +177,68 @@ def _worker_newest(rank, world, port, total, out):
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     start, _ = mdist.shard_range(total, rank, world)
-    envs = {mode: mdist.ShardedVecEnv(lambda n: FakeStackEnv(start, n), total, rank, world, gather_obs=mode)
+    envs = {mode: mdist.ShardedVecEnv(lambda n: FakeStackEnv(start, n, views), total, rank, world,
+                                      gather_obs=mode, stack_push=ref_stack_push)
             for mode in (True, 'newest')}
-    obs = {mode: [e.reset().clone()] for mode, e in envs.items()}
+    obs = {}
+    for mode, e in envs.items():
+        obs[mode] = [e.reset().clone()]
+    scal = {True: [], 'newest': []}
     g = torch.Generator().manual_seed(3)
     for t in range(12):
         actions = torch.randint(0, 18, (total,), generator=g, dtype=torch.int32)
         for mode, e in envs.items():
-            obs[mode].append(e.step(actions)[0].clone())
-    same = all(torch.equal(a, b) for a, b in zip(obs[True], obs['newest']))
+            o, rew, done, info = e.step(actions)
+            obs[mode].append(o.clone())
+            scal[mode].append(torch.stack([rew.float(), done.float(), info['eval_score'].float()]))
+    same = all(torch.equal(a, b) for a, b in zip(obs[True], obs['newest'])) and \
+        all(torch.equal(a, b) for a, b in zip(scal[True], scal['newest']))
     if rank == 1:
-        np.savez(out, same=np.array(same), last=obs['newest'][-1].numpy())
+        np.savez(out, same=np.array(same), last=obs['newest'][-1].numpy(), scal=scal['newest'][-1].numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('total', [8, 11])
-def test_newest_frame_gather_rebuilds_the_same_stacks(tmp_path, total):
-    """gather_obs='newest' (one frame per env on the wire) must give every rank
-    the same global observation as the full all-gather, through auto-resets and
-    with uneven shards; and the same as one process stepping everything."""
+@pytest.mark.parametrize('total,views', [(8, 1), (12, 1), (8, 2)])
+def test_newest_frame_gather_rebuilds_the_same_stacks(tmp_path, total, views):
+    """gather_obs='newest' (one frame per env and view on the wire, scalars in
+    one packed buffer) must give every rank the same global observation and
+    scalars as the full all-gather, through auto-resets; and the same as one
+    process stepping everything."""
     import torch
     import torch.multiprocessing as mp
     out = str(tmp_path / 'r1.npz')
-    mp.spawn(_worker_newest, args=(2, _free_port(), total, out), nprocs=2, join=True)
+    mp.spawn(_worker_newest, args=(2, _free_port(), total, views, out), nprocs=2, join=True)
     got = np.load(out)
     assert bool(got['same'])
-    env = FakeStackEnv(0, total)
+    env = FakeStackEnv(0, total, views)
     env.reset()
     g = torch.Generator().manual_seed(3)
     for t in range(12):
-        obs = env.step(torch.randint(0, 18, (total,), generator=g, dtype=torch.int32))[0]
+        obs, rew, done, info = env.step(torch.randint(0, 18, (total,), generator=g, dtype=torch.int32))
     assert np.array_equal(got['last'], obs.numpy())
+    assert np.array_equal(got['scal'], torch.stack([rew, done.float(), info['eval_score']]).numpy())
+
+
+def test_newest_mode_rejects_unsuitable_layouts_and_uneven_shards():
+    """LoRes3EA has the same (96, 96, 12) shape but mixes views
+    inside a pixel; it must be refused, not silently shifted wrongly."""
+    from magical_b200 import dist as mdist
+
+    class Env3EA(FakeStackEnv):
+        def __init__(self, n):
+            super().__init__(0, n)
+            self.preproc = 'LoRes3EA'
+
+    with pytest.raises(ValueError, match='LoRes3EA'):
+        mdist.ShardedVecEnv(lambda n: Env3EA(n), 8, 0, 2, gather_obs='newest')
+    with pytest.raises(ValueError, match='equal shards'):
+        mdist.ShardedVecEnv(lambda n: FakeStackEnv(0, n), 11, 0, 2, gather_obs='newest')
+
+
+def test_cuda_stack_push_refuses_cpu_tensors():
+    import torch
+    from magical_b200 import _native, dist as mdist
+    with pytest.raises(_native.NativeError):
+        mdist.cuda_stack_push(torch.zeros(2, 4, 4, 12, dtype=torch.uint8), torch.zeros(96, dtype=torch.uint8),
+                              None, 0, 2, 2, 0)

@@ -475,6 +475,34 @@ def test_pool_streaming_and_keep_scene(built):
     venv.close()
 
 
+def test_refresh_pool_defaults_never_overwrite_live_scenes(built):
+    """on a fresh handle (draw range = whole pool, resets drawn from
+    it) the first refresh_pool() may only narrow the draw range; the idle half
+    is replaced once an episode has passed, and no environment is ever bound to
+    an entry that is being overwritten."""
+    import torch
+    import magical_b200 as magical
+    env_id, batch = 'MoveToRegion-TestAll-LoRes4E-v0', 64
+    venv = magical.make_vec(env_id, batch, auto_reset=True, n_scenes=8, seed=3)
+    venv.reset()
+    bound = {int(venv.get_state(e)['scene']) for e in range(batch)}
+    assert max(bound) >= 4                       # envs do play the upper half
+    before = venv.scenes.copy()
+    assert venv.refresh_pool() == (0, 4)         # narrowed, nothing overwritten
+    assert np.array_equal(before.view(np.uint8), venv.scenes.view(np.uint8))
+    assert venv.refresh_pool() is None           # too early: envs still on 4..7
+    rng = np.random.RandomState(0)
+    for t in range(venv.max_episode_steps):
+        venv.step(torch.from_numpy(rng.randint(0, 18, size=batch).astype(np.int32)).cuda())
+    assert all(int(venv.get_state(e)['scene']) < 4 for e in range(batch))
+    assert venv.refresh_pool() == (4, 4)         # now the idle half is replaced
+    assert not np.array_equal(before[4:].view(np.uint8), venv.scenes[4:].view(np.uint8))
+    # host-side resets draw from the current range
+    venv.reset(env_ids=np.arange(10))
+    assert all(4 <= int(venv.get_state(e)['scene']) < 8 for e in range(10))
+    venv.close()
+
+
 def test_refresh_pool_from_background_sampler(built):
     """N1 streaming: worker processes sample layouts ahead of the GPU
     (pool_sampler.ScenePoolSampler); refresh_pool() swaps them into the idle

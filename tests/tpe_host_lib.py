@@ -44,6 +44,7 @@ def lib(max_surv=None):
         L.tpeh_reset.argtypes = [vp]
         L.tpeh_step.argtypes = [vp, i32]
         L.tpeh_get_state.argtypes = [vp, vp]
+        L.tpeh_set_state.argtypes = [vp, vp]
         L.tpeh_set_pose.argtypes = [vp, i32, f64, f64, f64]
         L.tpeh_kcon.argtypes = [vp]
         L.tpeh_words.argtypes = [vp]
@@ -77,6 +78,10 @@ class TpeHostEnv:
 
     def set_pose(self, body, x, y, angle):
         self._lib.tpeh_set_pose(self._h, body, x, y, angle)
+
+    def set_state(self, st):
+        st = np.ascontiguousarray(st, dtype=sc.state_dt)
+        assert self._lib.tpeh_set_state(self._h, st.ctypes.data) == 0
 
     def state(self):
         st = np.zeros((), dtype=sc.state_dt)
