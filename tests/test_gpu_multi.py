@@ -146,7 +146,7 @@ def _rank_main(rank, world, port, env_id, total, steps, pipeline, out_dir):
         obs, rew, done, info = env.step(acts)
         env.wait_obs()
         torch.cuda.synchronize()
-        if t % 7 == 0 or t >= steps - 3:
+        if t % 7 == 0 or t >= steps - 3 or 38 <= t <= 41:   # 39: the MoveToRegion episodes end (auto-reset)
             outs.append((t, obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy(),
                          info['eval_score'].cpu().numpy().copy()))
     np.savez(os.path.join(out_dir, f'rank{rank}.npz'), ts=np.array([o[0] for o in outs]),
