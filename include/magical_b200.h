@@ -335,6 +335,36 @@ int mg_synchronize(mg_handle* h);
  * (No reference counterpart: Chipmunk's arrays grow.) */
 int mg_overflow_count(mg_handle* h, int64_t* out);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Multi-GPU transport over NVLink peer memory (one process per GPU on one node).
+ * Each rank owns a region its peers map through CUDA IPC: barrier flags + `n_buffers` send buffers, each
+ * holding the rank's packed scalars and its newest frames ([views, shard, res, res, 3]).  Bind
+ * mg_comm_frame_ptr(c, b) with mg_bind_newest and let mg_step write reward / score / done into
+ * mg_comm_scalar_ptr(c, b) (layout is the caller's; the library only moves the bytes).  Per step:
+ *     mg_comm_barrier           every rank's send buffer b is complete and visible
+ *     mg_comm_gather_scalars    dst[world][scalar_bytes] <- every rank's scalars
+ *     mg_comm_stack_push        FlattenFrameStack of remote environments, frames read from the owners'
+ *                               buffers over NVLink inside the same kernel (all-gather fused with the rebuild)
+ * Rendezvous: mg_comm_export gives MG_COMM_HANDLE_BYTES bytes to exchange by any means (the Python host uses
+ * torch.distributed.all_gather); mg_comm_connect takes the world's handles in rank order.
+ * The barrier kernel gives up after 20 s (a dead peer must not hang the GPU); mg_comm_error then reports 1. */
+#define MG_COMM_HANDLE_BYTES 64
+typedef struct mg_comm mg_comm;
+int mg_comm_create(int32_t rank, int32_t world, int32_t n_buffers, int64_t scalar_bytes, int64_t frame_bytes,
+                   mg_comm** out);
+int mg_comm_export(mg_comm* c, void* handle_out);
+int mg_comm_connect(mg_comm* c, const void* all_handles);
+void* mg_comm_scalar_ptr(mg_comm* c, int32_t buffer);
+void* mg_comm_frame_ptr(mg_comm* c, int32_t buffer);
+int mg_comm_barrier(mg_comm* c, void* cuda_stream);
+int mg_comm_gather_scalars(mg_comm* c, int32_t buffer, void* dst_dev, void* cuda_stream);
+/* stacks_dev: u8 [n_global, res, res, 12] (one view plane); the frame of env e is read from rank e / shard at
+ * byte view_offset + (e % shard) * res * res * 3 of its frame buffer `buffer`. */
+int mg_comm_stack_push(mg_comm* c, int32_t buffer, int64_t view_offset, void* stacks_dev, const uint8_t* fresh_dev,
+                       int64_t env_first, int64_t env_count, int32_t shard, int32_t res, void* cuda_stream);
+int mg_comm_error(mg_comm* c, int32_t* out);
+int mg_comm_destroy(mg_comm* c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,8 @@
 from magical_b200.benchmarks import (  # noqa: F401
     ALL_REGISTERED_ENVS, AVAILABLE_PREPROCESSORS, DEMO_ENVS_TO_TEST_ENVS_MAP,
     EnvName, register_envs, update_magical_env_name)
-from magical_b200.env import MagicalEnv, make, make_task, make_vec  # noqa: F401
+from magical_b200.env import (MagicalEnv, make, make_task, make_vec,  # noqa: F401
+                              make_vec_mixed)
 from magical_b200.vec_env import MagicalVecEnv  # noqa: F401
 
 __version__ = '0.1.0'

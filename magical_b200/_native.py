@@ -21,7 +21,11 @@ ABI_SYMBOLS = [
     'mg_set_state', 'mg_set_pose', 'mg_launch_count', 'mg_synchronize', 'mg_update_scenes',
     'mg_set_draw_range', 'mg_overflow_count', 'mg_bind_obs_planes',
     'mg_newest_nbytes', 'mg_bind_newest', 'mg_stack_push', 'mg_step_render',
+    'mg_comm_create', 'mg_comm_export', 'mg_comm_connect', 'mg_comm_scalar_ptr',
+    'mg_comm_frame_ptr', 'mg_comm_barrier', 'mg_comm_gather_scalars',
+    'mg_comm_stack_push', 'mg_comm_error', 'mg_comm_destroy',
 ]
+COMM_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -64,6 +68,18 @@ def load():
     L.mg_newest_nbytes.argtypes = [vp]
     L.mg_bind_newest.argtypes = [vp, vp, i64]
     L.mg_stack_push.argtypes = [vp, vp, vp, i64, i64, i32, i64, i32, vp]
+    L.mg_comm_create.argtypes = [i32, i32, i32, i64, i64, ctypes.POINTER(vp)]
+    L.mg_comm_export.argtypes = [vp, vp]
+    L.mg_comm_connect.argtypes = [vp, vp]
+    L.mg_comm_scalar_ptr.restype = vp
+    L.mg_comm_scalar_ptr.argtypes = [vp, i32]
+    L.mg_comm_frame_ptr.restype = vp
+    L.mg_comm_frame_ptr.argtypes = [vp, i32]
+    L.mg_comm_barrier.argtypes = [vp, vp]
+    L.mg_comm_gather_scalars.argtypes = [vp, i32, vp, vp]
+    L.mg_comm_stack_push.argtypes = [vp, i32, i64, vp, vp, i64, i64, i32, i32, vp]
+    L.mg_comm_error.argtypes = [vp, vp]
+    L.mg_comm_destroy.argtypes = [vp]
     L.mg_score.argtypes = [vp, vp]
     L.mg_get_state.argtypes = [vp, i32, vp]
     L.mg_set_state.argtypes = [vp, i32, vp]

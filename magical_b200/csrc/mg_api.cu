@@ -77,6 +77,8 @@ struct mg_handle {
 
 static thread_local char g_err[512] = "";
 
+void mg_set_error_(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+
 static int fail(int code, const char* fmt, const char* detail) {
   snprintf(g_err, sizeof(g_err), fmt, detail ? detail : "");
   return code;

@@ -86,6 +86,95 @@ def cuda_stack_push(stacks, newest, fresh, env_first, env_count, shard,
         s.cuda_stream))
 
 
+class _DevMem:
+    """A raw device pointer presented through __cuda_array_interface__ so torch
+    can wrap it without copying."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {
+            'shape': (int(nbytes),), 'typestr': '|u1', 'data': (int(ptr), False),
+            'version': 2}
+
+
+class PeerTransport:
+    """NVLink peer-memory transport (`mg_comm_*`, csrc/mg_comm.cu): every
+    rank's send buffers live in a region its peers map through CUDA IPC, a
+    flag barrier replaces the collective's synchronisation, and the stack
+    rebuild kernel reads the frames straight from the owners' buffers."""
+
+    N_BUF = 2
+
+    def __init__(self, rank, world, n_local, views, hw, device, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from magical_b200 import _native
+        self._lib = _native.load()
+        self._check = _native.check
+        self.rank, self.world, self.n, self.views = rank, world, n_local, views
+        self.hw = hw
+        self.frame_bytes = hw[0] * hw[1] * 3
+        self.scalar_bytes = 12 * n_local + (-12 * n_local) % 16
+        fbytes = views * n_local * self.frame_bytes
+        assert fbytes % 16 == 0
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            self._check(self._lib.mg_comm_create(rank, world, self.N_BUF, self.scalar_bytes, fbytes,
+                                                 ctypes.byref(self._h)))
+            mine = (ctypes.c_uint8 * _native.COMM_HANDLE_BYTES)()
+            self._check(self._lib.mg_comm_export(self._h, mine))
+            send = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+            allh = torch.empty(world * _native.COMM_HANDLE_BYTES, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh, send, group=group)
+            host = allh.cpu().numpy().tobytes()
+            self._check(self._lib.mg_comm_connect(self._h, host))
+            dist.barrier(group=group)     # every rank has mapped every region before anyone signals
+            self._frames = [torch.as_tensor(_DevMem(self._lib.mg_comm_frame_ptr(self._h, k), fbytes),
+                                            device=device).view(views, n_local, hw[0], hw[1], 3)
+                            for k in range(self.N_BUF)]
+            self._scalars = [torch.as_tensor(_DevMem(self._lib.mg_comm_scalar_ptr(self._h, k), self.scalar_bytes),
+                                             device=device) for k in range(self.N_BUF)]
+        self._group = group
+
+    def frames(self, k):
+        return self._frames[k]
+
+    def scalars(self, k):
+        return self._scalars[k]
+
+    @staticmethod
+    def _stream():
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+
+    def barrier(self):
+        self._check(self._lib.mg_comm_barrier(self._h, self._stream()))
+
+    def gather_scalars(self, k, dst):
+        assert dst.is_contiguous() and dst.numel() == self.world * self.scalar_bytes
+        self._check(self._lib.mg_comm_gather_scalars(self._h, k, dst.data_ptr(), self._stream()))
+
+    def stack_push(self, k, view, stacks, fresh, first, count):
+        self._check(self._lib.mg_comm_stack_push(
+            self._h, k, view * self.n * self.frame_bytes, stacks.data_ptr(),
+            None if fresh is None else fresh.data_ptr(), int(first), int(count), self.n, self.hw[0],
+            self._stream()))
+
+    def error(self):
+        import ctypes
+        out = ctypes.c_int32(0)
+        self._check(self._lib.mg_comm_error(self._h, ctypes.byref(out)))
+        return int(out.value)
+
+    def close(self):
+        import torch.distributed as dist
+        if self._h:
+            self._frames = self._scalars = None
+            dist.barrier(group=self._group)   # nobody reads a region that is about to be freed
+            self._lib.mg_comm_destroy(self._h)
+            self._h = None
+
+
 class ShardedVecEnv:
     """A global batch of `total` envs split over the ranks of a process group.
 
@@ -105,7 +194,7 @@ class ShardedVecEnv:
     NEWEST_PREPROCS = ('LoRes4E', 'LoRes4A', 'LoResStack')
 
     def __init__(self, make_local_env, total, rank, world, gather_obs=False,
-                 group=None, pipeline=False, stack_push=None):
+                 group=None, pipeline=False, stack_push=None, transport='auto'):
         import torch
         self._torch = torch
         self.total, self.rank, self.world = total, rank, world
@@ -117,7 +206,14 @@ class ShardedVecEnv:
         self.group = group
         self.pipeline = bool(pipeline)
         self._stack_push = stack_push or cuda_stack_push
+        # 'p2p': NVLink peer memory (PeerTransport, gather fused into the stack
+        # rebuild kernel); 'nccl': ncclAllGather into a receive buffer +
+        # mg_stack_push; 'auto': p2p on CUDA, the collective elsewhere (gloo)
+        assert transport in ('auto', 'p2p', 'nccl')
+        self.transport = transport
+        self._peer = None
         self._t = 0
+        self.push_launches = 0   # k_stack_push launches so far (bench bookkeeping)
         self._newest_ready = False
         if gather_obs == 'newest' and world > 1:
             self._setup_newest()
@@ -153,28 +249,34 @@ class ShardedVecEnv:
         if self._bound:
             local.bind_obs(self._local_view)
         fshape = (self.views, n, H, W, 3)
-        self._send = [torch.zeros(fshape, dtype=torch.uint8, device=dev)
-                      for _ in range(2)]
-        self._recv = torch.zeros((self.world,) + fshape, dtype=torch.uint8,
-                                 device=dev)
         self._frame_bytes = H * W * 3
-        # packed scalars: [reward f32 n | score f32 n | done u8 n | pad 3n]
-        # (rows of 12n bytes keep the f32 views of the gathered rows aligned)
-        self._sc_send = torch.zeros(12 * n, dtype=torch.uint8, device=dev)
-        self._sc_recv = torch.zeros((self.world, 12 * n), dtype=torch.uint8,
-                                    device=dev)
-        self._sc_views = (self._sc_send[:4 * n].view(torch.float32),
-                          self._sc_send[8 * n:9 * n],
-                          self._sc_send[4 * n:8 * n].view(torch.float32))
+        if self.transport == 'auto':
+            self.transport = 'p2p' if self._cuda else 'nccl'
+        if self.transport == 'p2p':
+            self._peer = PeerTransport(self.rank, self.world, n, self.views, (H, W), dev, self.group)
+            self._send = [self._peer.frames(k) for k in range(2)]
+            self._sc_send = [self._peer.scalars(k) for k in range(2)]
+            row = self._peer.scalar_bytes
+        else:
+            self._send = [torch.zeros(fshape, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self._recv = torch.zeros((self.world,) + fshape, dtype=torch.uint8, device=dev)
+            row = 12 * n
+            self._sc_send = [torch.zeros(row, dtype=torch.uint8, device=dev) for _ in range(2)]
+        # packed scalars: [reward f32 n | score f32 n | done u8 n | pad]
+        # (rows of >= 12n bytes keep the f32 views of the gathered rows aligned)
+        self._sc_recv = torch.zeros((self.world, row), dtype=torch.uint8, device=dev)
+        self._sc_views = [(b[:4 * n].view(torch.float32), b[8 * n:9 * n], b[4 * n:8 * n].view(torch.float32))
+                          for b in self._sc_send]
         self._sc_bound = hasattr(local, 'bind_scalars')
-        if self._sc_bound:
-            local.bind_scalars(*self._sc_views)
         self._fresh = torch.zeros(self.total, dtype=torch.uint8, device=dev)
         if self._cuda:
-            self._comm = torch.cuda.Stream(device=dev)
+            # high priority: the tiny barrier / gather kernels must not queue
+            # behind thousands of physics and raster blocks
+            self._comm = torch.cuda.Stream(device=dev, priority=-1)
             self._ev_step = torch.cuda.Event()
             self._ev_ready = torch.cuda.Event()
             self._ev_send_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ev_barrier = [torch.cuda.Event(), torch.cuda.Event()]
             self._send_used = [False, False]
         self._newest_ready = True
 
@@ -207,45 +309,73 @@ class ShardedVecEnv:
         return all_gather_shards(obs, self.sizes, self.group)
 
     # --------------------------------------------------------------- step
-    def _exchange(self, send):
-        """All-gather the packed scalars and the newest frames, then fold the
-        frames into the remote shards' stacks (current stream)."""
+    def gather_only(self, k=0):
+        """The exchange of a step without the stack rebuild, on the current
+        stream: p2p = flag barrier + the peers' packed scalars; nccl = the two
+        all-gathers (packed scalars, newest frames)."""
         import torch.distributed as dist
+        if self._peer is not None:
+            self._peer.barrier()
+            if self._cuda:
+                self._ev_barrier[k].record(self._torch.cuda.current_stream())
+            self._peer.gather_scalars(k, self._sc_recv)
+            return
+        dist.all_gather_into_tensor(self._sc_recv.view(-1), self._sc_send[k], group=self.group)
+        dist.all_gather_into_tensor(self._recv.view(-1), self._send[k].view(-1), group=self.group)
+
+    def push_only(self, fresh=None, k=0):
+        """The stack rebuild of the remote shards on the current stream: p2p =
+        k_stack_push_p2p reading the owners' buffers over NVLink; nccl =
+        k_stack_push from the receive buffer."""
+        n = self.sizes[0]
+        rank_stride = self.views * n * self._frame_bytes
+        for v in range(self.views):
+            stacks = self._global[v] if self.views == 2 else self._global
+            for first, count in ((0, self.start), (self.stop, self.total - self.stop)):
+                if count <= 0:
+                    continue
+                if self._peer is not None:
+                    self._peer.stack_push(k, v, stacks, fresh, first, count)
+                else:
+                    newest = self._recv.view(-1)[v * n * self._frame_bytes:]
+                    self._stack_push(stacks, newest, fresh, first, count, n, rank_stride)
+                self.push_launches += 1
+
+    def _exchange(self, k):
+        """Exchange the packed scalars and the newest frames of send buffer k
+        and fold the frames into the remote shards' stacks (current stream)."""
         torch = self._torch
         n = self.sizes[0]
-        dist.all_gather_into_tensor(self._sc_recv.view(-1), self._sc_send,
-                                    group=self.group)
-        dist.all_gather_into_tensor(self._recv.view(-1), send.view(-1),
-                                    group=self.group)
+        self.gather_only(k)
         rew = self._sc_recv[:, :4 * n].view(torch.float32).reshape(-1)
         score = self._sc_recv[:, 4 * n:8 * n].view(torch.float32).reshape(-1)
         done = self._sc_recv[:, 8 * n:9 * n].reshape(-1)
         fresh = None
         if getattr(self.local, 'auto_reset', False):
             fresh = done
-        rank_stride = self.views * n * self._frame_bytes
-        for v in range(self.views):
-            stacks = self._global[v] if self.views == 2 else self._global
-            newest = self._recv.view(-1)[v * n * self._frame_bytes:]
-            for first, count in ((0, self.start),
-                                 (self.stop, self.total - self.stop)):
-                if count > 0:
-                    self._stack_push(stacks, newest, fresh, first, count, n,
-                                     rank_stride)
+        self.push_only(fresh, k)
         return rew, done, score
 
     def _step_newest(self, local_actions):
         torch = self._torch
         local = self.local
         k = self._t & 1
+        t = self._t
         self._t += 1
         send = self._send[k]
         if self._cuda:
             cur = torch.cuda.current_stream()
-            if self._send_used[k]:
-                cur.wait_event(self._ev_send_free[k])  # gather of step t-2
+            if t >= 2:
+                # send buffer k was last used by step t-2.  nccl: its gather has
+                # finished locally; p2p: the PEERS have finished reading it once
+                # this rank has passed the barrier of step t-1 (they enter that
+                # barrier only after their stack push of step t-2)
+                cur.wait_event(self._ev_barrier[1 - k] if self._peer is not None
+                               else self._ev_send_free[k])
         if hasattr(local, 'bind_newest'):
             local.bind_newest(send)
+        if self._sc_bound:
+            local.bind_scalars(*self._sc_views[k])
         obs, rew, done, info = local.step(local_actions)
         if not self._bound:
             self._local_view.copy_(obs)
@@ -255,19 +385,18 @@ class ShardedVecEnv:
             else:
                 send[0].copy_(obs[..., 9:])
         if not self._sc_bound:
-            r, d, s = self._sc_views
+            r, d, s = self._sc_views[k]
             r.copy_(rew)
             d.copy_(done)
             s.copy_(info['eval_score'])
         if not self._cuda:
-            rew, done, score = self._exchange(send)
+            rew, done, score = self._exchange(k)
             return self._global, rew, done, {'eval_score': score}
         self._ev_step.record(cur)
         with torch.cuda.stream(self._comm):
             self._comm.wait_event(self._ev_step)
-            rew, done, score = self._exchange(send)
+            rew, done, score = self._exchange(k)
             self._ev_send_free[k].record(self._comm)
-            self._send_used[k] = True
             self._ev_ready.record(self._comm)
         if not self.pipeline:
             cur.wait_event(self._ev_ready)
@@ -301,4 +430,8 @@ class ShardedVecEnv:
     def close(self):
         if self._newest_ready and getattr(self, '_cuda', False):
             self._torch.cuda.synchronize()
+        if self._peer is not None:
+            assert self._peer.error() == 0, 'peer barrier timed out (a rank died?)'
+            self._peer.close()
+            self._peer = None
         self.local.close()

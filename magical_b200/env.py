@@ -46,6 +46,30 @@ def make_vec(env_id, batch, device=0, auto_reset=True, n_scenes=None,
                          keep_scene=keep_scene)
 
 
+def make_vec_mixed(env_ids, batch, device=0, auto_reset=True, stream=None,
+                   alloc_obs=True, first_env=0, total=None):
+    """One batch holding several registered ids with the same preprocessor
+    (BASELINE config 5: all 8 Demo tasks in one batch).  The batch is cut into
+    len(env_ids) contiguous groups, group k plays env_ids[k] (contiguous so
+    that the warps of the physics kernel see one scene structure each); every
+    env restarts on its own task at auto-reset.  `first_env` / `total` place
+    this batch inside a larger, sharded global batch whose groups are defined
+    over `total` envs."""
+    made = [make_task(e) for e in env_ids]
+    preprocs = {spec.preproc for _, spec in made}
+    assert len(preprocs) == 1, f'one preprocessor per batch, got {preprocs}'
+    scenes = [task.build_scene() for task, _ in made]
+    total = batch if total is None else total
+    gids = (np.arange(first_env, first_env + batch) * len(env_ids)) // total
+    venv = MagicalVecEnv(made[0][0], batch, preproc=preprocs.pop(),
+                         device=device, auto_reset=auto_reset, scenes=scenes,
+                         stream=stream, alloc_obs=alloc_obs, keep_scene=True,
+                         default_scene_ids=gids)
+    venv.max_episode_steps = max(spec.max_episode_steps for _, spec in made)
+    venv.env_ids = list(env_ids)
+    return venv
+
+
 def make(env_id, device=0):
     """Single environment with the reference's gym call surface."""
     return MagicalEnv(env_id, device=device)

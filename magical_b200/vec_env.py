@@ -42,7 +42,7 @@ class MagicalVecEnv:
 
     def __init__(self, task, batch, preproc=None, device=0, auto_reset=True,
                  n_scenes=1, seed=None, scenes=None, stream=None,
-                 alloc_obs=True, keep_scene=False):
+                 alloc_obs=True, keep_scene=False, default_scene_ids=None):
         import torch
         if not torch.cuda.is_available():
             raise _native.NativeError(
@@ -72,6 +72,10 @@ class MagicalVecEnv:
         self._steps = 0
         self._draw_changed_at = 0
         self._all_in_range = False  # every env known to play a draw-range entry
+        # keep_scene batches (e.g. a mixed-task batch): env -> scene binding
+        # applied by a full reset() that names no scene ids
+        self.default_scene_ids = None if default_scene_ids is None else \
+            np.ascontiguousarray(default_scene_ids, dtype=np.int32)
         res = task.res_hw[0]
         cfg = _native.make_config(device=device, batch=self.batch,
                                   n_scenes=self.n_scenes, obs_mode=self.mode,
@@ -114,6 +118,9 @@ class MagicalVecEnv:
             env_ids = np.ascontiguousarray(env_ids, dtype=np.int32)
             n = len(env_ids)
             ids_p = env_ids.ctypes.data
+        if scene_ids is None and self.default_scene_ids is not None:
+            scene_ids = self.default_scene_ids if env_ids is None \
+                else self.default_scene_ids[env_ids]
         if scene_ids is None and self.n_scenes > 1 and self._draw[1] > 0:
             # host-side draws respect the draw range, like the device-side
             # redraw of an auto-reset does

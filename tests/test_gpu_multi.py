@@ -117,7 +117,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _rank_main(rank, world, port, env_id, total, steps, pipeline, out_dir):
+def _rank_main(rank, world, port, env_id, total, steps, pipeline, transport, out_dir):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -131,7 +131,8 @@ def _rank_main(rank, world, port, env_id, total, steps, pipeline, out_dir):
     env = mdist.ShardedVecEnv(
         lambda n: magical.make_vec(env_id, n, device=rank, auto_reset=True, seed=11, alloc_obs=False,
                                    keep_scene=True),
-        total, rank, world, gather_obs='newest', pipeline=pipeline)
+        total, rank, world, gather_obs='newest', pipeline=pipeline, transport=transport)
+    assert env.transport == transport
     n_sc = env.local.n_scenes
     if n_sc > 1:
         ids = np.arange(env.start, env.stop) % n_sc
@@ -157,19 +158,23 @@ def _rank_main(rank, world, port, env_id, total, steps, pipeline, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('env_id,total,steps,pipeline', [
-    ('MoveToRegion-Demo-LoRes4E-v0', 64, 48, False),        # 40-step episodes: one auto-reset inside
-    ('MoveToRegion-Demo-LoRes4E-v0', 64, 48, True),
-    ('MatchRegions-TestAll-LoResStack-v0', 48, 30, True),   # config 4's layout: two views, scene pool
+@pytest.mark.parametrize('env_id,total,steps,pipeline,transport', [
+    ('MoveToRegion-Demo-LoRes4E-v0', 64, 48, False, 'p2p'),   # 40-step episodes: one auto-reset inside
+    ('MoveToRegion-Demo-LoRes4E-v0', 64, 48, True, 'p2p'),
+    ('MatchRegions-TestAll-LoResStack-v0', 48, 30, True, 'p2p'),   # config 4's layout: two views, scene pool
+    ('MoveToRegion-Demo-LoRes4E-v0', 64, 48, True, 'nccl'),
+    ('MatchRegions-TestAll-LoResStack-v0', 48, 30, False, 'nccl'),
 ])
-def test_n_gpu_equals_one_gpu_bit_for_bit(built, tmp_path, env_id, total, steps, pipeline):
+def test_n_gpu_equals_one_gpu_bit_for_bit(built, tmp_path, env_id, total, steps, pipeline, transport):
+    """p2p: NVLink peer memory, frames read by the stack-rebuild kernel from the owners' buffers;
+    nccl: ncclAllGather + k_stack_push.  Either way every rank must hold the single-GPU result."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs >= 2 GPUs')
     import torch.multiprocessing as mp
     import magical_b200 as magical
     world = 2
-    mp.spawn(_rank_main, args=(world, _free_port(), env_id, total, steps, pipeline, str(tmp_path)),
+    mp.spawn(_rank_main, args=(world, _free_port(), env_id, total, steps, pipeline, transport, str(tmp_path)),
              nprocs=world, join=True)
     # the same global batch on ONE GPU
     venv = magical.make_vec(env_id, total, device=0, auto_reset=True, seed=11, keep_scene=True)

@@ -1,26 +1,41 @@
 #!/usr/bin/env python3
 """profiles/traffic.json from an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv`
-log of the bench workload: DRAM bytes (read + write) per launch of each kernel, averaged."""
+log of the bench workload: DRAM bytes (read + write) per launch of each kernel.
+
+The MEDIAN launch is reported, not the mean: the log also holds the reset render (k_raster with
+only_fresh = 1 touches 1/240 of the batch in the prelude) and cold first launches, which must not dilute the
+steady-state figure (the round-1 mean came out at 0.87x algorithmic where the
+steady-state launches are 1.146x)."""
 import collections
 import csv
 import json
+import statistics
 import sys
 
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
 hdr = rows[0]
-ki, mi, ui, vi = (hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Unit'),
-                  hdr.index('Metric Value'))
-scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-acc = collections.defaultdict(lambda: [0.0, 0])
+ii, ki, mi, ui, vi = (hdr.index('ID'), hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Unit'),
+                      hdr.index('Metric Value'))
+scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+per_launch = collections.defaultdict(lambda: collections.defaultdict(lambda: {'r': 0.0, 'w': 0.0}))
 for r in rows[1:]:
     if not r[mi].startswith('dram__bytes_'):
         continue
     name = r[ki].split('(')[0].split('<')[0].replace('void ', '').strip()
-    acc[name][0] += float(r[vi].replace(',', '')) * scale[r[ui]]
-    acc[name][1] += 1
-out = {k: v[0] / (v[1] / 2) for k, v in acc.items()}  # two metrics per launch
-out['_batch'] = 65536
-out['_env_id'] = 'ClusterColour-Demo-LoRes4E-v0'
+    per_launch[name][r[ii]]['r' if 'read' in r[mi] else 'w'] += float(r[vi].replace(',', '')) * scale[r[ui]]
+out, detail = {}, {}
+for name, launches in per_launch.items():
+    tot = sorted(v['r'] + v['w'] for v in launches.values())
+    med = statistics.median(tot)
+    out[name] = med
+    steady = [v for v in launches.values() if v['r'] + v['w'] >= 0.5 * med]
+    detail[name] = {'launches': len(tot), 'median_total': med,
+                    'median_read': statistics.median(v['r'] for v in steady),
+                    'median_write': statistics.median(v['w'] for v in steady),
+                    'min_total': tot[0], 'max_total': tot[-1]}
+out['_detail'] = detail
+out['_batch'] = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
+out['_env_id'] = sys.argv[4] if len(sys.argv) > 4 else 'ClusterColour-Demo-LoRes4E-v0'
 out['_source'] = sys.argv[2] if len(sys.argv) > 2 else sys.argv[1]
 json.dump(out, open('profiles/traffic.json', 'w'), indent=1)
 print(json.dumps(out, indent=1))
