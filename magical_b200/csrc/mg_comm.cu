@@ -8,9 +8,8 @@
  * every peer's flag slot, acquire-spin on the own slots) each rank runs
  *     k_peer_gather       the peers' packed scalars  -> a local [world, bytes] buffer      (12 B per env)
  *     k_stack_push_p2p    FlattenFrameStack of every REMOTE environment, the frame being read directly from
- *                         the owner's region over NVLink (24 lanes x 16 B = 384 contiguous bytes per warp,
- *                         re-distributed through shared memory) while the 48-byte stack groups stream
- *                         through local HBM
+ *                         the owner's region over NVLink (384 contiguous bytes per warp) while the 48-byte
+ *                         stack groups stream through local HBM
  * i.e. the all-gather and the stack rebuild are ONE kernel: no receive buffer, no NCCL kernel competing with
  * k_physics_tpe for shared memory, the NVLink transfer overlapped with the HBM work tile by tile.
  * Reference semantics: FlattenFrameStack.observation / reset, benchmarks/__init__.py:118-136.
@@ -71,7 +70,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 /* Cross-rank barrier: everything this rank's stream executed before is visible to the peers that pass it
  * (kernel boundaries write back to L2, the point of coherence peers read through), and everything the peers
  * executed before THEIR barrier is visible to kernels launched after this one (fresh L1). */
-__global__ void k_xbarrier(PeerPtrs peers, int rank, int world, uint32_t epoch, unsigned long long timeout_ns,
+__global__ void k_xbarrier(const __grid_constant__ PeerPtrs peers, int rank, int world, uint32_t epoch, unsigned long long timeout_ns,
                            uint32_t* err) {
   const int q = threadIdx.x;
   if (q >= world || q == rank) return;
@@ -87,7 +86,7 @@ __global__ void k_xbarrier(PeerPtrs peers, int rank, int world, uint32_t epoch, 
 
 /* dst[r][0..bytes) <- peer r's region at `offset` (16-byte units), all ranks incl. the own one */
 __global__ void __launch_bounds__(256)
-k_peer_gather(PeerPtrs peers, int64_t offset, uint4* __restrict__ dst, int64_t n16) {
+k_peer_gather(const __grid_constant__ PeerPtrs peers, int64_t offset, uint4* __restrict__ dst, int64_t n16) {
   const int r = blockIdx.y;
   const uint4* src = reinterpret_cast<const uint4*>(peers.p[r] + offset);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
@@ -95,40 +94,29 @@ k_peer_gather(PeerPtrs peers, int64_t offset, uint4* __restrict__ dst, int64_t n
 }
 
 /* FlattenFrameStack of the remote environments [env_first, env_first + count), frames read from the owners'
- * regions.  One thread = 4 pixels = 48 B of stack + 12 B of frame; one warp = 384 contiguous frame bytes. */
+ * regions.  One thread = 4 pixels = 48 B of stack + 12 B of frame; a warp reads 384 contiguous frame bytes
+ * over NVLink (three non-coherent 32-bit loads per lane: the second and third hit the 128-byte lines the
+ * first one brought into L1; the buffers are read-only while the kernel runs, L1 is fresh at every launch).
+ * No shared memory and ~32 registers, so its blocks fit into the registers k_physics_tpe leaves free (that
+ * kernel is bound by shared memory at 4 warps per SM) and the NVLink + HBM streaming hides under the next
+ * step's physics.  The remote loads are issued first and consumed last: the NVLink round trip (~3 us) overlaps
+ * the HBM read of the stack. */
 __global__ void __launch_bounds__(256)
-k_stack_push_p2p(uint8_t* __restrict__ stacks, PeerPtrs peers, int64_t frames_offset /* of this buffer + view */,
+k_stack_push_p2p(uint8_t* __restrict__ stacks, const __grid_constant__ PeerPtrs peers, int64_t frames_offset /* of this buffer + view */,
                  const uint8_t* __restrict__ fresh, long long env_first, long long n_groups_total, int groups_per_env,
                  int shard) {
-  __shared__ uint32_t s_fr[8][96];
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  /* groups_per_env is a multiple of 32, so a warp never straddles two environments */
-  const long long gw = g - lane;
-  const bool warp_live = gw < n_groups_total;
-  long long env = 0;
-  int gi = 0;
-  if (warp_live) {
-    env = env_first + gw / groups_per_env;
-    gi = (int)(gw % groups_per_env);
-    const uint8_t* src = peers.p[env / shard] + frames_offset + ((env % shard) * (long long)groups_per_env + gi) * 12;
-    if (lane < 24) {
-      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src) + lane);
-      *reinterpret_cast<uint4*>(&s_fr[wid][lane * 4]) = v;
-    }
-  }
-  __syncwarp();
-  if (!warp_live || g >= n_groups_total) return;
-  const uint32_t n0 = s_fr[wid][3 * lane], n1 = s_fr[wid][3 * lane + 1], n2 = s_fr[wid][3 * lane + 2];
-  const uint32_t col[4] = {n0 & 0xFFFFFFu, (n0 >> 24) | ((n1 & 0xFFFFu) << 8), (n1 >> 16) | ((n2 & 0xFFu) << 16), n2 >> 8};
-  uint4* sp = reinterpret_cast<uint4*>(stacks + (env * groups_per_env + gi + lane) * 48);
-  uint32_t w[12];
+  if (g >= n_groups_total) return;
+  const long long env = env_first + g / groups_per_env;
+  const int gi = (int)(g % groups_per_env);
+  const uint32_t* np_ = reinterpret_cast<const uint32_t*>(peers.p[env / shard] + frames_offset +
+                                                          ((env % shard) * (long long)groups_per_env + gi) * 12);
+  const uint32_t n0 = __ldg(np_), n1 = __ldg(np_ + 1), n2 = __ldg(np_ + 2);
+  uint4* sp = reinterpret_cast<uint4*>(stacks + (env * groups_per_env + gi) * 48);
+  const uint4 a = __ldcs(sp), b = __ldcs(sp + 1), c = __ldcs(sp + 2); /* evict-first: stream past the L2-resident physics state */
   const bool f = fresh != nullptr && fresh[env] != 0;
-  if (!f) {
-    const uint4 a = sp[0], b = sp[1], c = sp[2];
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
-  }
+  uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+  const uint32_t col[4] = {n0 & 0xFFFFFFu, (n0 >> 24) | ((n1 & 0xFFFFu) << 8), (n1 >> 16) | ((n2 & 0xFFu) << 16), n2 >> 8};
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const uint32_t n = col[i];

@@ -54,6 +54,20 @@
 #define RASTER_MIN_BLOCKS 4
 #endif
 
+#ifdef RASTER_PROF
+__device__ unsigned long long g_rprof[16];
+#define RPROF_DECL long long rp_t = clock64();
+#define RPROF(i) do { if (threadIdx.x == 0) { long long n_ = clock64(); atomicAdd(&g_rprof[i], (unsigned long long)(n_ - rp_t)); rp_t = n_; } } while (0)
+#else
+#define RPROF_DECL
+#define RPROF(i) ((void)0)
+#endif
+#ifdef RASTER_PROF
+#define RCOUNT(i, n) atomicAdd(&g_rprof[i], (unsigned long long)(n))
+#else
+#define RCOUNT(i, n) ((void)0)
+#endif
+
 struct RPrim {
   uint32_t rgb;         /* bits 0..23 colour; bit 24: stippled line */
   uint16_t e0;          /* first edge (polygons) / first of the 2 float4 of a line segment */
@@ -208,6 +222,7 @@ __device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restr
 template <int SS>
 __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& sc, int view, int res_out, int ecap,
                            int scap, int* s_off /* [2*MG_MAX_PRIMS+2] */, int* s_misc) {
+  RPROF_DECL
   const int tid = threadIdx.x, nt = blockDim.x;
   const int np = sc.n_prims;
   const int res_full = res_out * SS;
@@ -246,6 +261,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   for (int i = tid; i < RGRID * RGRID * vs.rwords; i += nt) vs.tiles[i] = 0u;
   for (int i = tid; i < RGRID * RGRID; i += nt) vs.cover[i] = -1;
   __syncthreads();
+  RPROF(0);
   const int nv = s_misc[0];
   const int nrp = s_misc[1];
   /* B: window-space vertices */
@@ -255,6 +271,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     vs.verts[v] = prim_vertex(st, sc, sc.prims[lo], v - s_off[lo], cam);
   }
   __syncthreads();
+  RPROF(1);
   /* C: per-primitive records: bounding box in samples (the oracle's loop bounds), winding */
   for (int p = tid; p < np; p += nt) {
     const mg_prim_t& pr = sc.prims[p];
@@ -323,6 +340,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     }
   }
   __syncthreads();
+  RPROF(2);
   /* D: span-table offsets (warp 0) + oriented edge equations and, per polygon edge, the sample rows it
    * can bound: row j is bounded by an edge only if j + 0.5 lies within one sample of the edge's own
    * y-extent (the polygon is convex, so edges further away hold with a margin far above fp32 rounding) */
@@ -391,6 +409,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     vs.eaux[v] = make_float4(-B * inv, -C * inv, __int_as_float(j0), __int_as_float(cnt >= RSHORT ? cnt : 0));
   }
   __syncthreads();
+  RPROF(3);
   /* E0: warp 0 turns the per-edge row counts into offsets (exclusive prefix) while the other warps
    * initialise the span table: polygons start from their bounding columns (rows outside the vertices'
    * y-extent are empty), thick line segments are solved directly per row */
@@ -435,6 +454,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     }
   }
   __syncthreads();
+  RPROF(4);
   /* E1: one work item per (polygon edge, row it can bound): the exact first / last covered column w.r.t.
    * that edge, folded into the row's span with a compare-and-swap.  Every edge function is monotone in x,
    * so the covered set of a row is [max of the lower bounds, min of the upper bounds] -- the same set a
@@ -511,6 +531,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     }
   }
   __syncthreads();
+  RPROF(5);
   /* F: tile bins from the spans: one work item per (primitive, tile row) */
   const int TS = (res_out / RGRID) * SS; /* samples per tile side */
   const int npairs = s_misc[6];
@@ -545,6 +566,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     }
   }
   __syncthreads();
+  RPROF(6);
 }
 
 /* round-half-even mean of SSxSS samples (cv2 INTER_AREA: saturate_cast<uchar>(sum / 16.f)) */
@@ -582,6 +604,7 @@ __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int t
       bits &= ~(1u << b);
       const int p = w * 32 + b;
       const RPrim& R = vs.prims[p];
+      RCOUNT(10, 1);
       uint32_t m[4];
       if (p == cover) {
 #pragma unroll
@@ -715,51 +738,185 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   for (int v = 0; v < NV; v++) {
     int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
     build_view<SS>(vsm[v], st, sc, view, res_out, ecap, scap, s_off, s_misc);
-    if (threadIdx.x == 0) s_misc[4] = 0; /* next tile to hand out */
+    if (threadIdx.x == 0) { s_misc[4] = 0; s_misc[5] = 0; } /* flat / busy list lengths */
     __syncthreads();
   }
+  RPROF_DECL
   const int T = res_out / RGRID;        /* output pixels per tile side (multiple of 4) */
   const int gpr = T / 4;                /* 4-pixel groups per tile row */
   const int gpt = gpr * T;              /* groups per tile */
   const size_t frame_px = (size_t)res_out * res_out;
-  /* half-warps own tiles: all 16 lanes walk the same primitive list */
-  const int hw_id = threadIdx.x >> 4, hl = threadIdx.x & 15;
-  const int n_hw = blockDim.x >> 4;
-
-  /* tiles are handed out dynamically (flat tiles cost a fraction of busy ones) */
-  const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
-  (void)hw_id; (void)n_hw;
-  for (;;) {
-    int tile = 0;
-    if (hl == 0) tile = atomicAdd(&s_misc[4], 1);
-    tile = __shfl_sync(hmask, tile, 0, 16);
-    if (tile >= RGRID * RGRID) break;
-    const int tx = tile % RGRID, ty = tile / RGRID; /* ty counts GL rows (bottom-up) */
-    /* per tile and view: the covering primitive, which mask words hold primitives above it, and whether
-     * the whole tile is one flat colour (nothing above the cover / nothing at all) */
-    int cover[NV];
-    uint32_t words[NV], flat_col[NV];
-    bool flat[NV];
+  /* G0: one thread per tile: the covering primitive, which mask words hold primitives above it, and whether
+   * the whole tile is one flat colour (nothing above the cover / nothing at all) -> tile descriptor
+   *   bits 0..8 cover + 1 | bits 9..16 non-empty mask words above the cover | bit 31 flat
+   * and the tile goes on the flat list or the busy list.  The lists reuse s_off (dead after E1). */
+  uint8_t* const flat_list = reinterpret_cast<uint8_t*>(s_off);
+  uint8_t* const busy_list = flat_list + RGRID * RGRID;
+  for (int tile = threadIdx.x; tile < RGRID * RGRID; tile += blockDim.x) {
+    bool all_flat = true;
 #pragma unroll
     for (int v = 0; v < NV; v++) {
-      cover[v] = vsm[v].cover[tile];
+      const int cover = vsm[v].cover[tile];
       const uint32_t* tm = vsm[v].tiles + tile * vsm[v].rwords;
       uint32_t wm = 0u, above = 0u;
       for (int w = 0; w < vsm[v].rwords; w++) {
         uint32_t bits = tm[w];
-        if (cover[v] >= 0) {
-          if ((cover[v] >> 5) > w) bits = 0u;
-          else if ((cover[v] >> 5) == w) bits &= ~((1u << (cover[v] & 31)) - 1u);
+        if (cover >= 0) {
+          if ((cover >> 5) > w) bits = 0u;
+          else if ((cover >> 5) == w) bits &= ~((1u << (cover & 31)) - 1u);
         }
         if (bits) wm |= 1u << w;
         uint32_t others = bits;
-        if (cover[v] >= 0 && (cover[v] >> 5) == w) others &= ~(1u << (cover[v] & 31));
+        if (cover >= 0 && (cover >> 5) == w) others &= ~(1u << (cover & 31));
         above |= others;
       }
-      words[v] = wm;
-      flat[v] = (above == 0u);
-      uint32_t c = (cover[v] >= 0) ? (vsm[v].prims[cover[v]].rgb & 0xFFFFFFu) : (BG_R | (BG_G << 8) | (BG_B << 16));
-      flat_col[v] = c;
+      vsm[v].cover[tile] = (int32_t)((uint32_t)(cover + 1) | (wm << 9) | (above == 0u ? 0x80000000u : 0u));
+      all_flat = all_flat && (above == 0u);
+    }
+    if (all_flat) flat_list[atomicAdd(&s_misc[4], 1)] = (uint8_t)tile;
+    else busy_list[atomicAdd(&s_misc[5], 1)] = (uint8_t)tile;
+  }
+  __syncthreads();
+  const int n_flat = s_misc[4], n_busy = s_misc[5];
+  __syncthreads(); /* s_misc[4] becomes the busy-tile hand-out counter */
+  if (threadIdx.x == 0) s_misc[4] = 0;
+  RCOUNT(8, threadIdx.x == 0 ? n_flat : 0); RCOUNT(9, threadIdx.x == 0 ? n_busy : 0);
+
+  /* G1: flat tiles, all threads converged: item = (flat tile, 4-pixel group) */
+  for (int item = threadIdx.x; item < n_flat * gpt; item += blockDim.x) {
+    const int tile = flat_list[item / gpt], g = item % gpt;
+    const int tx = tile % RGRID, ty = tile / RGRID; /* ty counts GL rows (bottom-up) */
+      const int Yg = ty * T + g / gpr;
+      const int X0 = tx * T + (g % gpr) * 4;
+      const int Y = res_out - 1 - Yg;       /* output row, 0 = top */
+      /* issue the read of the surviving frames before shading so HBM latency overlaps the ALU work */
+      uint4 pre[NV][3];
+      if ((MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_LORES3EA) &&
+          !fresh) {
+#pragma unroll
+        for (int v = 0; v < 1; v++) {
+          const size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * plane_stride : 0;
+          const uint4* ptr =
+              reinterpret_cast<const uint4*>(obs + plane + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
+          /* streaming accesses: every byte of the stack is touched exactly once per step */
+          pre[v][0] = __ldcs(ptr); pre[v][1] = __ldcs(ptr + 1); pre[v][2] = __ldcs(ptr + 2);
+        }
+      }
+    uint32_t col[NV][4];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const int cover = (int)((uint32_t)vsm[v].cover[tile] & 0x1FFu) - 1;
+      const uint32_t c = (cover >= 0) ? (vsm[v].prims[cover].rgb & 0xFFFFFFu) : (BG_R | (BG_G << 8) | (BG_B << 16));
+#pragma unroll
+      for (int i = 0; i < 4; i++) col[v][i] = c;
+    }
+      if (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK) {
+        /* [B, R, R, 12] (LoResStack: [2, B, R, R, 12]): 4 pixels = 48 bytes = 3 x uint4 */
+#pragma unroll
+        for (int v = 0; v < 1; v++) {
+          const size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * plane_stride : 0;
+          uint4* ptr = reinterpret_cast<uint4*>(obs + plane + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
+          uint32_t w[12];
+          if (!fresh) {
+            uint4 a = pre[v][0], b = pre[v][1], c = pre[v][2];
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) stack_push(&w[3 * i], col[v][i], fresh, push != 0);
+          __stcs(ptr, make_uint4(w[0], w[1], w[2], w[3]));
+          __stcs(ptr + 1, make_uint4(w[4], w[5], w[6], w[7]));
+          __stcs(ptr + 2, make_uint4(w[8], w[9], w[10], w[11]));
+          if (newest) {
+            /* newest frame alone, [views][batch][R][R][3]: the send buffer of the multi-GPU observation
+             * gather (27 648 B per environment instead of the 110 592 B stack) */
+            uint32_t* np_ = reinterpret_cast<uint32_t*>(
+                newest + (((MODE == MG_OBS_LORESSTACK ? (size_t)pass * batch : 0) + env) * frame_px + (size_t)Y * res_out + X0) * 3);
+            const uint32_t c0 = col[v][0], c1 = col[v][1], c2 = col[v][2], c3 = col[v][3];
+            __stcs(np_, c0 | (c1 << 24));
+            __stcs(np_ + 1, (c1 >> 8) | (c2 << 16));
+            __stcs(np_ + 2, (c2 >> 16) | (c3 << 8));
+          }
+        }
+      } else if (MODE == MG_OBS_LORES3EA) {
+        /* bytes 0..2 = newest allo frame; bytes 3..11 = 3 ego frames, oldest first */
+        uint4* ptr = reinterpret_cast<uint4*>(obs + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
+        uint32_t w[12];
+        if (!fresh) {
+          uint4 a = pre[0][0], b = pre[0][1], c = pre[0][2];
+          w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+          w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          uint32_t al = col[0][i], eg = col[NV - 1][i];
+          if (fresh) {
+            w[3 * i] = al | (eg << 24);
+            w[3 * i + 1] = (eg >> 8) | (eg << 16);
+            w[3 * i + 2] = (eg >> 16) | (eg << 8);
+          } else if (!push) {
+            w[3 * i] = al | (w[3 * i] & 0xFF000000u);
+            w[3 * i + 2] = (w[3 * i + 2] & 0xFFu) | (eg << 8);
+          } else {
+            uint32_t w1 = w[3 * i + 1], w2 = w[3 * i + 2];
+            uint32_t b6 = (w1 >> 16) & 0xFF, b7 = (w1 >> 24) & 0xFF;
+            w[3 * i] = al | (b6 << 24);          /* old bytes 6..11 -> 3..8 ; new ego -> 9..11 */
+            w[3 * i + 1] = b7 | (w2 << 8);
+            w[3 * i + 2] = (w2 >> 24) | (eg << 8);
+          }
+        }
+        __stcs(ptr, make_uint4(w[0], w[1], w[2], w[3]));
+        __stcs(ptr + 1, make_uint4(w[4], w[5], w[6], w[7]));
+        __stcs(ptr + 2, make_uint4(w[8], w[9], w[10], w[11]));
+      } else if (MODE == MG_OBS_LORESCHW4E) {
+        /* [B, 12, R, R]: plane c of frame f is channel 3f + c; 4 pixels = one u32 per plane */
+        uint8_t* base = obs + (size_t)env * 12 * frame_px + (size_t)Y * res_out + X0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          uint32_t nw = ((col[0][0] >> (8 * c)) & 0xFF) | (((col[0][1] >> (8 * c)) & 0xFF) << 8) |
+                        (((col[0][2] >> (8 * c)) & 0xFF) << 16) | (((col[0][3] >> (8 * c)) & 0xFF) << 24);
+          uint32_t* p0 = reinterpret_cast<uint32_t*>(base + (size_t)(0 + c) * frame_px);
+          uint32_t* p1 = reinterpret_cast<uint32_t*>(base + (size_t)(3 + c) * frame_px);
+          uint32_t* p2 = reinterpret_cast<uint32_t*>(base + (size_t)(6 + c) * frame_px);
+          uint32_t* p3 = reinterpret_cast<uint32_t*>(base + (size_t)(9 + c) * frame_px);
+          if (fresh) { *p0 = nw; *p1 = nw; *p2 = nw; *p3 = nw; }
+          else if (!push) { *p3 = nw; }
+          else { uint32_t a = *p1, b = *p2, d = *p3; *p0 = a; *p1 = b; *p2 = d; *p3 = nw; }
+        }
+      } else {
+        /* RAW [2, B, R, R, 3]: 4 pixels = 12 bytes = 3 x u32 */
+#pragma unroll
+        for (int v = 0; v < 1; v++) {
+          uint32_t* ptr = reinterpret_cast<uint32_t*>(
+              obs + (size_t)pass * plane_stride + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 3);
+          uint32_t c0 = col[v][0], c1 = col[v][1], c2 = col[v][2], c3 = col[v][3];
+          ptr[0] = c0 | (c1 << 24);
+          ptr[1] = (c1 >> 8) | (c2 << 16);
+          ptr[2] = (c2 >> 16) | (c3 << 8);
+        }
+      }
+  }
+  __syncthreads(); /* the hand-out counter is reset */
+
+  /* G2: busy tiles, handed out dynamically to half-warps: all 16 lanes walk the same primitive list */
+  const int hl = threadIdx.x & 15;
+  const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+  for (;;) {
+    int bi = 0;
+    if (hl == 0) bi = atomicAdd(&s_misc[4], 1);
+    bi = __shfl_sync(hmask, bi, 0, 16);
+    if (bi >= n_busy) break;
+    const int tile = busy_list[bi];
+    const int tx = tile % RGRID, ty = tile / RGRID;
+    int cover[NV];
+    uint32_t words[NV];
+    bool flat[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const uint32_t d = (uint32_t)vsm[v].cover[tile];
+      cover[v] = (int)(d & 0x1FFu) - 1;
+      words[v] = (d >> 9) & 0xFFu;
+      flat[v] = (d >> 31) != 0u;
     }
     for (int g = hl; g < gpt; g += 16) {
       const int Yg = ty * T + g / gpr;
@@ -782,13 +939,13 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
 #pragma unroll
       for (int v = 0; v < NV; v++) {
         if (flat[v]) {
+          const uint32_t c = (cover[v] >= 0) ? (vsm[v].prims[cover[v]].rgb & 0xFFFFFFu) : (BG_R | (BG_G << 8) | (BG_B << 16));
 #pragma unroll
-          for (int i = 0; i < 4; i++) col[v][i] = flat_col[v];
+          for (int i = 0; i < 4; i++) col[v][i] = c;
         } else {
           shade4<SS>(vsm[v], X0, Yg, tile, cover[v], words[v], px_scale, col[v]);
         }
       }
-
       if (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK) {
         /* [B, R, R, 12] (LoResStack: [2, B, R, R, 12]): 4 pixels = 48 bytes = 3 x uint4 */
 #pragma unroll
@@ -877,6 +1034,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
     }
   }
   __syncthreads(); /* the next pass rebuilds the shared tables */
+  RPROF(7);
   } /* pass */
   if (threadIdx.x == 0 && fresh) stg.fresh = 0;
 }
@@ -892,6 +1050,13 @@ size_t mg_raster_smem_bytes(int mode, int ecap, int scap, int rcap) {
                     sizeof(int32_t) * RGRID * RGRID;
   return per_view * n_views(mode);
 }
+
+#ifdef RASTER_PROF
+extern "C" void mg_raster_prof_read(unsigned long long* out16, int reset) {
+  cudaMemcpyFromSymbol(out16, g_rprof, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_rprof, z, sizeof(z)); }
+}
+#endif
 
 cudaError_t mg_raster_upload_units(const double* units /* [130][2] */) {
   return cudaMemcpyToSymbol(c_unit, units, sizeof(double) * 130 * 2);

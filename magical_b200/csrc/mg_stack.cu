@@ -32,7 +32,7 @@ k_stack_push(uint8_t* __restrict__ stacks, const uint8_t* __restrict__ newest, c
   uint32_t w[12];
   const bool f = fresh != nullptr && fresh[env] != 0;
   if (!f) {
-    const uint4 a = sp[0], b = sp[1], c = sp[2];
+    const uint4 a = __ldcs(sp), b = __ldcs(sp + 1), c = __ldcs(sp + 2); /* evict-first: stream past the L2-resident physics state */
     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
     w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
   }

@@ -270,9 +270,14 @@ class ShardedVecEnv:
         self._sc_bound = hasattr(local, 'bind_scalars')
         self._fresh = torch.zeros(self.total, dtype=torch.uint8, device=dev)
         if self._cuda:
-            # high priority: the tiny barrier / gather kernels must not queue
-            # behind thousands of physics and raster blocks
-            self._comm = torch.cuda.Stream(device=dev, priority=-1)
+            # high priority: the exchange is enqueued AFTER the next step's
+            # k_physics_tpe, whose queued blocks would otherwise all be placed
+            # first.  That kernel is bound by shared memory (4 one-warp blocks
+            # per SM); the stack-push blocks use no shared memory and fill the
+            # registers it leaves free, so both run at full residency.
+            import os
+            prio = int(os.environ.get('MG_COMM_PRIORITY', '-1'))
+            self._comm = torch.cuda.Stream(device=dev, priority=prio)
             self._ev_step = torch.cuda.Event()
             self._ev_ready = torch.cuda.Event()
             self._ev_send_free = [torch.cuda.Event(), torch.cuda.Event()]
