@@ -177,6 +177,8 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
     host[i].s = scenes[i];
     const char* why = mg_build_scene_aux(&scenes[i], &host[i].aux);
     if (why) return fail(MG_E_INVALID, "mg_create: scene rejected: %s", why);
+    why = mg_build_raster_aux(&scenes[i], &host[i].ra);
+    if (why) return fail(MG_E_INVALID, "mg_create: scene rejected: %s", why);
     int edges = 0, rprims = 0, rows = 0;
     const char* bad = scene_raster_needs(scenes[i], res_full, &edges, &rprims, &rows);
     if (bad) return fail(MG_E_INVALID, "mg_create: %s", bad);
@@ -569,6 +571,8 @@ int mg_update_scenes(mg_handle* h, int32_t first, int32_t n, const mg_scene_t* s
   for (int i = 0; i < n; i++) {
     host[i].s = scenes[i];
     const char* why = mg_build_scene_aux(&scenes[i], &host[i].aux);
+    if (why) return fail(MG_E_INVALID, "mg_update_scenes: scene rejected: %s", why);
+    why = mg_build_raster_aux(&scenes[i], &host[i].ra);
     if (why) return fail(MG_E_INVALID, "mg_update_scenes: scene rejected: %s", why);
     int edges = 0, rprims = 0, rows = 0;
     const char* bad = scene_raster_needs(scenes[i], h->res_out * ss, &edges, &rprims, &rows);

@@ -10,6 +10,7 @@
 
 #include "../../include/magical_b200.h"
 #include "mg_scene_aux.h"
+#include "mg_raster_aux.h"
 
 #define MG_NCACHE 48 /* cached contacts: this sub-step's (<= 32) + those of pairs that collided in the last 3 sub-steps;
                         at most 64 (the thread-per-environment kernel tracks matched entries in a 64-bit mask) */
@@ -45,6 +46,7 @@ struct __align__(16) EnvState {
 struct DeviceScene {
   mg_scene_t s;
   mg_scene_aux_t aux;
+  mg_raster_aux_t ra;
 };
 
 #endif

@@ -39,10 +39,9 @@
 #define RGRID 12           /* tiles per side */
 #define RMAXP 192          /* window-space primitives (draw prims + expanded line segments) */
 #define RWORDS (RMAXP / 32)
-#define RLONG 512          /* capacity of the compact long-edge list (>= 2 * MG_MAX_PRIMS + 2) */
-#ifndef RSHORT
-#define RSHORT 12          /* polygon edges bounding fewer rows than this are processed one edge per lane */
-#endif
+#define RLONG MG_RLONG      /* capacity of the compact long-edge list */
+#define RSHORT MG_RSHORT   /* polygon edges bounding fewer rows than this are processed one edge per lane */
+#define RMAXLINES 16       /* thick line segments whose rows are spread over all warps (more: per-warp fallback) */
 #define BG_R 231
 #define BG_G 231
 #define BG_B 234
@@ -114,15 +113,10 @@ __device__ __forceinline__ Camera make_camera(const EnvState& st, const mg_scene
   return cam;
 }
 
-/* window-space vertex k of draw primitive pr */
-__device__ __forceinline__ float2 prim_vertex(const EnvState& st, const mg_scene_t& sc, const mg_prim_t& pr, int k,
+/* window-space vertex of draw primitive pr whose local-space coordinates are (vx, vy) (static table ra.lv) */
+__device__ __forceinline__ float2 prim_vertex(const EnvState& st, const mg_prim_t& pr, float vx, float vy,
                                               const Camera& cam) {
-  float vx, vy;
   if (pr.kind == MG_PRIM_NGON) {
-    const double* U = c_unit[unit_offset(pr.nvert) + k];
-    double r = (double)pr.radius;
-    vx = (float)__dmul_rn(U[0], r);
-    vy = (float)__dmul_rn(U[1], r);
     if (pr.xform == MG_XFORM_PUPIL) {
       int b = pr.body, e = pr.body2;
       float pc = (float)__dadd_rn(__dmul_rn(st.R[e].x, st.R[b].x), __dmul_rn(st.R[e].y, st.R[b].y));
@@ -135,8 +129,6 @@ __device__ __forceinline__ float2 prim_vertex(const EnvState& st, const mg_scene
     float2 w = body_to_world(st, pr.body, vx, vy);
     return world_to_px(cam, w.x, w.y);
   }
-  vx = sc.dverts[pr.vert0 + k][0];
-  vy = sc.dverts[pr.vert0 + k][1];
   float2 w = make_float2(vx, vy);
   if (pr.xform == MG_XFORM_BODY) w = body_to_world(st, pr.body, vx, vy);
   return world_to_px(cam, w.x, w.y);
@@ -192,26 +184,32 @@ __device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restr
   if (L < 0.0f) {
     hi = lo - 1;
   } else {
-    /* along in [0, L] */
-    if (ux > 0.0f) {
-      lo = first_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
-      if (lo <= hi) hi = last_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
-    } else if (ux < 0.0f) {
-      hi = last_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
-      if (lo <= hi) lo = first_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
-    } else if (ca < 0.0f || ca > L) {
+    /* The covered set is the intersection of four half-lines (each bound is monotone in x), so the order in
+     * which they are intersected does not matter.  perp in [-hw, hw] first: for the thin borders it leaves a
+     * sample or two, and the along bounds are then usually settled by evaluating the two end columns. */
+    if (uy > 0.0f) {
+      lo = first_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
+      if (lo <= hi) hi = last_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
+    } else if (uy < 0.0f) {
+      hi = last_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
+      if (lo <= hi) lo = first_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
+    } else if (fabsf(cp) > hw) {
       hi = lo - 1;
     }
-    /* perp in [-hw, hw] */
+    /* along in [0, L] */
     if (lo <= hi) {
-      if (uy > 0.0f) {
-        lo = first_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
-        if (lo <= hi) hi = last_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
-      } else if (uy < 0.0f) {
-        hi = last_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
-        if (lo <= hi) lo = first_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
-      } else if (fabsf(cp) > hw) {
-        hi = lo - 1;
+      const float a0 = along(lo), a1 = along(hi);
+      const bool in0 = !(a0 < 0.0f) && !(a0 > L), in1 = !(a1 < 0.0f) && !(a1 > L);
+      if (!(in0 && in1)) { /* (monotone: both ends inside => every column between them is) */
+        if (ux > 0.0f) {
+          lo = first_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
+          if (lo <= hi) hi = last_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
+        } else if (ux < 0.0f) {
+          hi = last_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
+          if (lo <= hi) lo = first_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
+        } else if (ca < 0.0f || ca > L) {
+          hi = lo - 1;
+        }
       }
     }
   }
@@ -220,63 +218,32 @@ __device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restr
 
 /* Build the window-space primitive set, span table and tile bins of one view. */
 template <int SS>
-__device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& sc, int view, int res_out, int ecap,
-                           int scap, int* s_off /* [2*MG_MAX_PRIMS+2] */, int* s_misc) {
+__device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& sc, const mg_raster_aux_t& ra, int view,
+                           int res_out, int ecap, int scap, int* s_off /* [RLONG] */, int* s_misc) {
   RPROF_DECL
   const int tid = threadIdx.x, nt = blockDim.x;
   const int np = sc.n_prims;
   const int res_full = res_out * SS;
   const Camera cam = make_camera(st, sc, view, res_full);
   const float px_scale = (float)res_full / 384.0f;
-  /* A: vertex offsets and window-prim indices (a line loop expands to one prim per segment) */
-  if (tid < 32) {
-    /* warp 0: exclusive prefix sums of (vertex count, window-primitive count) over the draw list */
-    int off = 0, rp = 0;
-    for (int base = 0; base < np; base += 32) {
-      int p = base + tid;
-      int nvv = 0, nrr = 0;
-      if (p < np) {
-        nvv = sc.prims[p].nvert;
-        nrr = (sc.prims[p].kind == MG_PRIM_LINELOOP) ? nvv : 1;
-      }
-      int iv = nvv, ir = nrr;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int tv = __shfl_up_sync(0xffffffffu, iv, d), tr = __shfl_up_sync(0xffffffffu, ir, d);
-        if (tid >= d) { iv += tv; ir += tr; }
-      }
-      if (p < np) {
-        s_off[p] = off + iv - nvv;
-        s_off[MG_MAX_PRIMS + 1 + p] = rp + ir - nrr;
-      }
-      off += __shfl_sync(0xffffffffu, iv, 31);
-      rp += __shfl_sync(0xffffffffu, ir, 31);
-    }
-    if (tid == 0) {
-      s_off[np] = off;
-      s_misc[0] = off > ecap ? ecap : off;
-      s_misc[1] = rp > vs.rcap ? vs.rcap : rp;
-    }
-  }
+  /* vertex offsets, window-primitive indices and the vertex -> primitive map are static per scene (ra) */
+  const int nv = min((int)ra.nv, ecap);
+  const int nrp = min((int)ra.nrp, vs.rcap);
   for (int i = tid; i < RGRID * RGRID * vs.rwords; i += nt) vs.tiles[i] = 0u;
   for (int i = tid; i < RGRID * RGRID; i += nt) vs.cover[i] = -1;
-  __syncthreads();
-  RPROF(0);
-  const int nv = s_misc[0];
-  const int nrp = s_misc[1];
+  if (tid == 0) s_misc[7] = 0; /* number of thick line segments collected by phase C */
   /* B: window-space vertices */
   for (int v = tid; v < nv; v += nt) {
-    int lo = 0, hi = np - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= v) lo = mid; else hi = mid - 1; }
-    vs.verts[v] = prim_vertex(st, sc, sc.prims[lo], v - s_off[lo], cam);
+    const float2 l = *reinterpret_cast<const float2*>(ra.lv[v]);
+    vs.verts[v] = prim_vertex(st, sc.prims[ra.vprim[v]], l.x, l.y, cam);
   }
   __syncthreads();
   RPROF(1);
   /* C: per-primitive records: bounding box in samples (the oracle's loop bounds), winding */
   for (int p = tid; p < np; p += nt) {
     const mg_prim_t& pr = sc.prims[p];
-    int v0 = s_off[p], n = pr.nvert;
-    int rp0 = s_off[MG_MAX_PRIMS + 1 + p];
+    int v0 = ra.voff[p], n = pr.nvert;
+    int rp0 = ra.rp0[p];
     if (v0 + n > nv) continue;
     uint32_t rgb = pr.rgb[0] | (pr.rgb[1] << 8) | (pr.rgb[2] << 16);
     if (pr.kind == MG_PRIM_LINELOOP) {
@@ -346,11 +313,12 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
    * y-extent (the polygon is convex, so edges further away hold with a margin far above fp32 rounding) */
   if (tid < 32) {
     const int TSd = (res_out / RGRID) * SS; /* samples per tile side */
-    int off = 0, toff = 0;
+    int off = 0, toff = 0, nlines = 0;
     for (int base = 0; base < nrp; base += 32) {
       int p = base + tid;
       int nr = (p < nrp) ? vs.prims[p].nrows : 0;
       int r0 = (p < nrp) ? vs.prims[p].row0 : 0;
+      const bool is_line = (p < nrp) && vs.prims[p].ne == 0 && nr > 0;
       /* tile rows the primitive's sample rows touch = its work items in the binning pass (F) */
       int nt_rows = (nr > 0) ? (min((r0 + nr - 1) / TSd, RGRID - 1) - r0 / TSd + 1) : 0;
       int incl = nr, tincl = nt_rows;
@@ -365,22 +333,28 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         vs.prims[p].span0 = start;
         vs.prims[p].tile0 = toff + tincl - nt_rows;
       }
+      /* thick line segments with rows: their (segment, row) items are spread over all warps in E0 */
+      const unsigned lm = __ballot_sync(0xffffffffu, is_line && nr > 0);
+      if (is_line && nr > 0) {
+        const int k = nlines + __popc(lm & ((1u << tid) - 1u));
+        if (k < RMAXLINES) s_off[RLONG - RMAXLINES + k] = p;
+      }
+      nlines += __popc(lm);
       off += __shfl_sync(0xffffffffu, incl, 31);
       toff += __shfl_sync(0xffffffffu, tincl, 31);
     }
-    if (tid == 0) { s_misc[2] = off > scap ? scap : off; s_misc[6] = toff; }
+    if (tid == 0) { s_misc[2] = off > scap ? scap : off; s_misc[6] = toff; s_misc[7] = nlines; }
   }
   for (int v = tid; v < nv; v += nt) {
-    int lo = 0, hi = np - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_off[mid] <= v) lo = mid; else hi = mid - 1; }
-    const mg_prim_t& pr = sc.prims[lo];
-    int rp0 = s_off[MG_MAX_PRIMS + 1 + lo];
+    const int dp = ra.vprim[v];
+    const mg_prim_t& pr = sc.prims[dp];
+    int rp0 = ra.rp0[dp];
     if (pr.kind == MG_PRIM_LINELOOP || rp0 >= vs.rcap) {
       vs.eaux[v] = make_float4(0.0f, 0.0f, __int_as_float(0), __int_as_float(0));
       vs.edges[v] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(0));
       continue;
     }
-    int v0 = s_off[lo], n = pr.nvert, k = v - v0;
+    int v0 = ra.voff[dp], n = pr.nvert, k = v - v0;
     float2 a = vs.verts[v0 + k], b = vs.verts[v0 + (k + 1) % n];
     const RPrim& R = vs.prims[rp0];
     float sgn = R.sgn;
@@ -405,19 +379,24 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     const int cnt = j1 >= j0 ? j1 - j0 + 1 : 0;
     /* edges.w = primitive | rows << 8;  eaux.w = rows that enter the item queue (long edges only: the
      * short ones -- the sides of the many-gons -- are handled one edge per lane) */
-    vs.edges[v] = make_float4(A, B, C, __int_as_float(rp0 | (cnt << 8)));
-    vs.eaux[v] = make_float4(-B * inv, -C * inv, __int_as_float(j0), __int_as_float(cnt >= RSHORT ? cnt : 0));
+    /* long = enters the item queue: only edges on the static candidate list can (every other edge, however
+     * many rows it bounds at an unusual resolution, takes the one-edge-per-lane path) */
+    const bool lng = cnt >= RSHORT && ra.vcand[v] != 0;
+    vs.edges[v] = make_float4(A, B, C, __int_as_float(rp0 | (cnt << 8) | (lng ? (1 << 30) : 0)));
+    vs.eaux[v] = make_float4(-B * inv, -C * inv, __int_as_float(j0), __int_as_float(lng ? cnt : 0));
   }
   __syncthreads();
   RPROF(3);
-  /* E0: warp 0 turns the per-edge row counts into offsets (exclusive prefix) while the other warps
-   * initialise the span table: polygons start from their bounding columns (rows outside the vertices'
-   * y-extent are empty), thick line segments are solved directly per row */
+  /* E0: warp 0 turns the row counts of the edges that can be long (static candidate list) into item offsets
+   * (exclusive prefix) while the other warps initialise the span table: polygons start from their bounding
+   * columns (rows outside the vertices' y-extent are empty), thick line segments are solved directly per row */
   const int nwarp = nt >> 5, wid = tid >> 5, lane = tid & 31;
   if (wid == 0) {
     int off = 0, nlong = 0;
-    for (int base = 0; base < nv; base += 32) {
-      int v = base + lane;
+    const int ncand = ra.n_cand;
+    for (int base = 0; base < ncand; base += 32) {
+      const int ci = base + lane;
+      const int v = (ci < ncand) ? (int)ra.cand[ci] : nv;
       int c = (v < nv) ? __float_as_int(vs.eaux[v].w) : 0;
       int incl = c;
 #pragma unroll
@@ -428,17 +407,19 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
       const int start = off + incl - c;
       if (v < nv) vs.eaux[v].w = __int_as_float(start);
       off += __shfl_sync(0xffffffffu, incl, 31);
-      /* compact list of the edges that own items: item offset << 10 | edge (most table entries -- sides of the
-       * many-gons, line vertices -- own none and would otherwise be walked over by every lane) */
+      /* compact list of the edges that own items: item offset << 12 | edge (MG_RV_MAX <= 4096) */
       const unsigned has = __ballot_sync(0xffffffffu, c > 0);
       const int k = nlong + __popc(has & ((1u << lane) - 1u));
-      if (c > 0 && k < RLONG) s_off[k] = (start << 10) | v;
+      if (c > 0 && k < RLONG - RMAXLINES) s_off[k] = (start << 12) | v;
       nlong += __popc(has);
     }
-    if (lane == 0) { s_misc[3] = off; s_misc[5] = nlong; }
+    if (lane == 0) { s_misc[3] = off; s_misc[5] = min(nlong, RLONG - RMAXLINES); }
   } else {
+    const int nlines = s_misc[7];
+    const bool spread = nlines <= RMAXLINES;
     for (int p = wid - 1; p < nrp; p += nwarp - 1) {
       const RPrim R = vs.prims[p];
+      if (R.ne == 0 && spread) continue;
       for (int r = lane; r < R.nrows; r += 32) {
         const int j = R.row0 + r;
         short2 sp;
@@ -450,6 +431,21 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
           sp = row_span(R, vs.edges, vs.eaux, j);
         }
         vs.spans[R.span0 + r] = sp;
+      }
+    }
+    if (spread && nlines > 0) {
+      /* (segment, row) items of the thick line segments, spread evenly over the 7 warps */
+      int total = 0;
+      for (int k = 0; k < nlines; k++) total += vs.prims[s_off[RLONG - RMAXLINES + k]].nrows;
+      for (int it = tid - 32; it < total; it += nt - 32) {
+        int k = 0, r = it;
+        for (;;) {
+          const int nr = vs.prims[s_off[RLONG - RMAXLINES + k]].nrows;
+          if (r < nr) break;
+          r -= nr; k++;
+        }
+        const RPrim& R = vs.prims[s_off[RLONG - RMAXLINES + k]];
+        vs.spans[R.span0 + r] = row_span(R, vs.edges, vs.eaux, R.row0 + r);
       }
     }
   }
@@ -498,24 +494,14 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     const int it_end = min((wid + 1) * chunk, n_items);
     int it = wid * chunk + lane;
     const int nlong = s_misc[5];
-    if (it < it_end && nlong <= RLONG && nv <= 1024) {
+    if (it < it_end) {
       /* the long edge holding item `it`: last list entry whose offset is <= it */
       int lo = 0, hi = nlong - 1;
-      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((s_off[mid] >> 10) <= it) lo = mid; else hi = mid - 1; }
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((s_off[mid] >> 12) <= it) lo = mid; else hi = mid - 1; }
       int k = lo;
       for (; it < it_end; it += 32) {
-        while (k + 1 < nlong && (s_off[k + 1] >> 10) <= it) k++;
-        const int e = s_off[k] & 1023;
-        const float4 X = vs.eaux[e];
-        fold(vs.edges[e], X, __float_as_int(X.z) + (it - __float_as_int(X.w)));
-      }
-    } else if (it < it_end) {
-      /* list overflow (never with the registered scenes): walk the full edge table */
-      int lo = 0, hi = nv - 1;
-      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (__float_as_int(vs.eaux[mid].w) <= it) lo = mid; else hi = mid - 1; }
-      int e = lo;
-      for (; it < it_end; it += 32) {
-        while (e + 1 < nv && __float_as_int(vs.eaux[e + 1].w) <= it) e++;
+        while (k + 1 < nlong && (s_off[k + 1] >> 12) <= it) k++;
+        const int e = s_off[k] & 4095;
         const float4 X = vs.eaux[e];
         fold(vs.edges[e], X, __float_as_int(X.z) + (it - __float_as_int(X.w)));
       }
@@ -523,8 +509,8 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     /* short edges: one edge per lane, a handful of rows each */
     for (int v = tid; v < nv; v += nt) {
       const float4 E = vs.edges[v];
-      const int cnt = __float_as_int(E.w) >> 8;
-      if (cnt <= 0 || cnt >= RSHORT) continue;
+      const int cnt = (__float_as_int(E.w) >> 8) & 0x3FFF;
+      if (cnt <= 0 || ((__float_as_int(E.w) >> 30) & 1)) continue;
       const float4 X = vs.eaux[v];
       const int j0 = __float_as_int(X.z);
       for (int r = 0; r < cnt; r++) fold(E, X, j0 + r);
@@ -707,7 +693,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   constexpr int NV = (MODE == MG_OBS_LORES3EA) ? 2 : 1;
   constexpr int NPASS = SEQ ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_off[RLONG]; /* prefix tables of phase A..D (2 * MG_MAX_PRIMS + 2 ints), then the long-edge list */
+  __shared__ int s_off[RLONG]; /* long-edge list; last RMAXLINES entries: thick line segments; later the tile lists */
   __shared__ int s_misc[8];
   const int env = env0 + blockIdx.x; /* this launch covers environments [env0, env0 + gridDim.x) */
   if (env >= batch) return;
@@ -737,7 +723,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   for (int pass = 0; pass < NPASS; pass++) {
   for (int v = 0; v < NV; v++) {
     int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
-    build_view<SS>(vsm[v], st, sc, view, res_out, ecap, scap, s_off, s_misc);
+    build_view<SS>(vsm[v], st, sc, scenes[st.scene].ra, view, res_out, ecap, scap, s_off, s_misc);
     if (threadIdx.x == 0) { s_misc[4] = 0; s_misc[5] = 0; } /* flat / busy list lengths */
     __syncthreads();
   }
