@@ -61,7 +61,7 @@ __device__ unsigned long long g_rprof[16];
 #define RPROF_DECL
 #define RPROF(i) ((void)0)
 #endif
-#ifdef RASTER_PROF
+#if defined(RASTER_PROF) && defined(RASTER_COUNT)
 #define RCOUNT(i, n) atomicAdd(&g_rprof[i], (unsigned long long)(n))
 #else
 #define RCOUNT(i, n) ((void)0)
@@ -555,16 +555,16 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   RPROF(6);
 }
 
-/* round-half-even mean of SSxSS samples (cv2 INTER_AREA: saturate_cast<uchar>(sum / 16.f)) */
+/* round-half-even mean of SSxSS samples (cv2 INTER_AREA: saturate_cast<uchar>(sum / 16.f)), red and blue
+ * together: (s + 7 + (bit 4 of s)) >> 4 rounds s / 16 to nearest, ties to even, and never carries out of a
+ * 12-bit field (s <= 4080) */
 template <int SS>
-__device__ __forceinline__ uint32_t finish_colour(uint32_t sr, uint32_t sg, uint32_t sb) {
+__device__ __forceinline__ uint32_t finish_colour(uint32_t srb, uint32_t sg) {
   if (SS == 4) {
-    uint32_t q, rem;
-    q = sr >> 4; rem = sr & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sr = q;
-    q = sg >> 4; rem = sg & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sg = q;
-    q = sb >> 4; rem = sb & 15; if (rem > 8 || (rem == 8 && (q & 1))) q++; sb = q;
+    srb = ((srb + 0x00070007u + ((srb >> 4) & 0x00010001u)) >> 4) & 0x00FF00FFu;
+    sg = (sg + 7u + ((sg >> 4) & 1u)) >> 4;
   }
-  return sr | (sg << 8) | (sb << 16);
+  return srb | (sg << 8);
 }
 
 /* Colours of the 4 output pixels (X0..X0+3, Yg): front-to-back walk over the tile's primitives.
@@ -576,7 +576,9 @@ __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int t
    * row3 -> 20..23  (two packed 16-sample strips per word, so a pixel's mask is two shift+and pairs) */
   constexpr uint32_t FULLM = (SS == 4) ? 0x00FF00FFu : 1u;
   uint32_t unres[4] = {FULLM, FULLM, FULLM, FULLM};
-  uint32_t sr[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  /* colour sums of the 16 samples, two channels per word: red in bits 0..11, blue in bits 16..27 (a sum is at
+   * most 16 * 255 < 4096), green on its own */
+  uint32_t srb[4] = {0, 0, 0, 0}, sg[4] = {0, 0, 0, 0};
   const uint32_t* tm = vs.tiles + tile * vs.rwords;
   const int x0 = X0 * SS, y0 = Yg * SS;
   uint32_t any = FULLM;
@@ -643,12 +645,12 @@ __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int t
           }
         }
       }
-      const uint32_t cr = R.rgb & 0xFF, cg = (R.rgb >> 8) & 0xFF, cb = (R.rgb >> 16) & 0xFF;
+      const uint32_t crb = R.rgb & 0x00FF00FFu, cg = (R.rgb >> 8) & 0xFF;
       any = 0u;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         uint32_t cnt = __popc(m[i]);
-        sr[i] += cnt * cr; sg[i] += cnt * cg; sb[i] += cnt * cb;
+        srb[i] += cnt * crb; sg[i] += cnt * cg;
         unres[i] &= ~m[i];
         any |= unres[i];
       }
@@ -657,7 +659,7 @@ __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int t
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     uint32_t cnt = __popc(unres[i]);
-    out[i] = finish_colour<SS>(sr[i] + cnt * BG_R, sg[i] + cnt * BG_G, sb[i] + cnt * BG_B);
+    out[i] = finish_colour<SS>(srb[i] + cnt * (BG_R | (BG_B << 16)), sg[i] + cnt * BG_G);
   }
 }
 
@@ -724,7 +726,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   for (int v = 0; v < NV; v++) {
     int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
     build_view<SS>(vsm[v], st, sc, scenes[st.scene].ra, view, res_out, ecap, scap, s_off, s_misc);
-    if (threadIdx.x == 0) { s_misc[4] = 0; s_misc[5] = 0; } /* flat / busy list lengths */
+    if (threadIdx.x == 0) { s_misc[4] = 0; s_misc[5] = 0; s_misc[6] = 0; } /* flat / heavy / light list lengths */
     __syncthreads();
   }
   RPROF_DECL
@@ -740,6 +742,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   uint8_t* const busy_list = flat_list + RGRID * RGRID;
   for (int tile = threadIdx.x; tile < RGRID * RGRID; tile += blockDim.x) {
     bool all_flat = true;
+    int weight = 0; /* primitives a pixel of this tile may have to walk */
 #pragma unroll
     for (int v = 0; v < NV; v++) {
       const int cover = vsm[v].cover[tile];
@@ -752,6 +755,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           else if ((cover >> 5) == w) bits &= ~((1u << (cover & 31)) - 1u);
         }
         if (bits) wm |= 1u << w;
+        weight += __popc(bits);
         uint32_t others = bits;
         if (cover >= 0 && (cover >> 5) == w) others &= ~(1u << (cover & 31));
         above |= others;
@@ -759,24 +763,22 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       vsm[v].cover[tile] = (int32_t)((uint32_t)(cover + 1) | (wm << 9) | (above == 0u ? 0x80000000u : 0u));
       all_flat = all_flat && (above == 0u);
     }
+    /* busy tiles: the heavy ones (robot, piled-up blocks) fill the list from the front and are handed out
+     * first, the light ones from the back: longest-processing-time-first keeps the tail of G2 short */
     if (all_flat) flat_list[atomicAdd(&s_misc[4], 1)] = (uint8_t)tile;
-    else busy_list[atomicAdd(&s_misc[5], 1)] = (uint8_t)tile;
+    else if (weight >= 5) busy_list[atomicAdd(&s_misc[5], 1)] = (uint8_t)tile;
+    else busy_list[RGRID * RGRID - 1 - atomicAdd(&s_misc[6], 1)] = (uint8_t)tile;
   }
   __syncthreads();
-  const int n_flat = s_misc[4], n_busy = s_misc[5];
+  const int n_flat = s_misc[4], n_heavy = s_misc[5], n_busy = n_heavy + s_misc[6];
   __syncthreads(); /* s_misc[4] becomes the busy-tile hand-out counter */
   if (threadIdx.x == 0) s_misc[4] = 0;
+  RPROF(8);
   RCOUNT(8, threadIdx.x == 0 ? n_flat : 0); RCOUNT(9, threadIdx.x == 0 ? n_busy : 0);
 
-  /* G1: flat tiles, all threads converged: item = (flat tile, 4-pixel group) */
-  for (int item = threadIdx.x; item < n_flat * gpt; item += blockDim.x) {
-    const int tile = flat_list[item / gpt], g = item % gpt;
-    const int tx = tile % RGRID, ty = tile / RGRID; /* ty counts GL rows (bottom-up) */
-      const int Yg = ty * T + g / gpr;
-      const int X0 = tx * T + (g % gpr) * 4;
-      const int Y = res_out - 1 - Yg;       /* output row, 0 = top */
+  /* read the surviving frames of one 4-pixel group / shift, append and write it back */
+  auto load_pre = [&](int X0, int Y, uint4 (&pre)[NV][3]) {
       /* issue the read of the surviving frames before shading so HBM latency overlaps the ALU work */
-      uint4 pre[NV][3];
       if ((MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_LORES3EA) &&
           !fresh) {
 #pragma unroll
@@ -788,14 +790,8 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           pre[v][0] = __ldcs(ptr); pre[v][1] = __ldcs(ptr + 1); pre[v][2] = __ldcs(ptr + 2);
         }
       }
-    uint32_t col[NV][4];
-#pragma unroll
-    for (int v = 0; v < NV; v++) {
-      const int cover = (int)((uint32_t)vsm[v].cover[tile] & 0x1FFu) - 1;
-      const uint32_t c = (cover >= 0) ? (vsm[v].prims[cover].rgb & 0xFFFFFFu) : (BG_R | (BG_G << 8) | (BG_B << 16));
-#pragma unroll
-      for (int i = 0; i < 4; i++) col[v][i] = c;
-    }
+  };
+  auto store_group = [&](int X0, int Y, const uint4 (&pre)[NV][3], const uint32_t (&col)[NV][4]) {
       if (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK) {
         /* [B, R, R, 12] (LoResStack: [2, B, R, R, 12]): 4 pixels = 48 bytes = 3 x uint4 */
 #pragma unroll
@@ -881,8 +877,46 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           ptr[2] = (c2 >> 16) | (c3 << 8);
         }
       }
+  };
+
+  /* G1: flat tiles, all threads converged: item = (flat tile, 4-pixel group).  The loads of the next item are
+   * issued before the current one is written back (two groups in flight per thread). */
+  {
+    const int n_items = n_flat * gpt;
+    int item = threadIdx.x;
+    uint4 pre_next[NV][3];
+    auto item_xy = [&](int it, int& X0, int& Y, int& tile) {
+      tile = flat_list[it / gpt];
+      const int g = it % gpt;
+      const int tx = tile % RGRID, ty = tile / RGRID; /* ty counts GL rows (bottom-up) */
+      X0 = tx * T + (g % gpr) * 4;
+      Y = res_out - 1 - (ty * T + g / gpr);
+    };
+    int X0 = 0, Y = 0, tile = 0;
+    if (item < n_items) { item_xy(item, X0, Y, tile); load_pre(X0, Y, pre_next); }
+    while (item < n_items) {
+      uint4 pre[NV][3];
+#pragma unroll
+      for (int v = 0; v < NV; v++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) pre[v][k] = pre_next[v][k];
+      const int cX0 = X0, cY = Y, ctile = tile;
+      const int next = item + blockDim.x;
+      if (next < n_items) { item_xy(next, X0, Y, tile); load_pre(X0, Y, pre_next); }
+      uint32_t col[NV][4];
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        const int cover = (int)((uint32_t)vsm[v].cover[ctile] & 0x1FFu) - 1;
+        const uint32_t c = (cover >= 0) ? (vsm[v].prims[cover].rgb & 0xFFFFFFu) : (BG_R | (BG_G << 8) | (BG_B << 16));
+#pragma unroll
+        for (int i = 0; i < 4; i++) col[v][i] = c;
+      }
+      store_group(cX0, cY, pre, col);
+      item = next;
+    }
   }
   __syncthreads(); /* the hand-out counter is reset */
+  RPROF(9);
 
   /* G2: busy tiles, handed out dynamically to half-warps: all 16 lanes walk the same primitive list */
   const int hl = threadIdx.x & 15;
@@ -892,7 +926,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
     if (hl == 0) bi = atomicAdd(&s_misc[4], 1);
     bi = __shfl_sync(hmask, bi, 0, 16);
     if (bi >= n_busy) break;
-    const int tile = busy_list[bi];
+    const int tile = busy_list[bi < n_heavy ? bi : RGRID * RGRID - 1 - (bi - n_heavy)];
     const int tx = tile % RGRID, ty = tile / RGRID;
     int cover[NV];
     uint32_t words[NV];
@@ -910,17 +944,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       const int Y = res_out - 1 - Yg;       /* output row, 0 = top */
       /* issue the read of the surviving frames before shading so HBM latency overlaps the ALU work */
       uint4 pre[NV][3];
-      if ((MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_LORES3EA) &&
-          !fresh) {
-#pragma unroll
-        for (int v = 0; v < 1; v++) {
-          const size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * plane_stride : 0;
-          const uint4* ptr =
-              reinterpret_cast<const uint4*>(obs + plane + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
-          /* streaming accesses: every byte of the stack is touched exactly once per step */
-          pre[v][0] = __ldcs(ptr); pre[v][1] = __ldcs(ptr + 1); pre[v][2] = __ldcs(ptr + 2);
-        }
-      }
+      load_pre(X0, Y, pre);
       uint32_t col[NV][4];
 #pragma unroll
       for (int v = 0; v < NV; v++) {
@@ -932,91 +956,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           shade4<SS>(vsm[v], X0, Yg, tile, cover[v], words[v], px_scale, col[v]);
         }
       }
-      if (MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK) {
-        /* [B, R, R, 12] (LoResStack: [2, B, R, R, 12]): 4 pixels = 48 bytes = 3 x uint4 */
-#pragma unroll
-        for (int v = 0; v < 1; v++) {
-          const size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * plane_stride : 0;
-          uint4* ptr = reinterpret_cast<uint4*>(obs + plane + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
-          uint32_t w[12];
-          if (!fresh) {
-            uint4 a = pre[v][0], b = pre[v][1], c = pre[v][2];
-            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-            w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
-          }
-#pragma unroll
-          for (int i = 0; i < 4; i++) stack_push(&w[3 * i], col[v][i], fresh, push != 0);
-          __stcs(ptr, make_uint4(w[0], w[1], w[2], w[3]));
-          __stcs(ptr + 1, make_uint4(w[4], w[5], w[6], w[7]));
-          __stcs(ptr + 2, make_uint4(w[8], w[9], w[10], w[11]));
-          if (newest) {
-            /* newest frame alone, [views][batch][R][R][3]: the send buffer of the multi-GPU observation
-             * gather (27 648 B per environment instead of the 110 592 B stack) */
-            uint32_t* np_ = reinterpret_cast<uint32_t*>(
-                newest + (((MODE == MG_OBS_LORESSTACK ? (size_t)pass * batch : 0) + env) * frame_px + (size_t)Y * res_out + X0) * 3);
-            const uint32_t c0 = col[v][0], c1 = col[v][1], c2 = col[v][2], c3 = col[v][3];
-            __stcs(np_, c0 | (c1 << 24));
-            __stcs(np_ + 1, (c1 >> 8) | (c2 << 16));
-            __stcs(np_ + 2, (c2 >> 16) | (c3 << 8));
-          }
-        }
-      } else if (MODE == MG_OBS_LORES3EA) {
-        /* bytes 0..2 = newest allo frame; bytes 3..11 = 3 ego frames, oldest first */
-        uint4* ptr = reinterpret_cast<uint4*>(obs + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
-        uint32_t w[12];
-        if (!fresh) {
-          uint4 a = pre[0][0], b = pre[0][1], c = pre[0][2];
-          w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-          w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          uint32_t al = col[0][i], eg = col[NV - 1][i];
-          if (fresh) {
-            w[3 * i] = al | (eg << 24);
-            w[3 * i + 1] = (eg >> 8) | (eg << 16);
-            w[3 * i + 2] = (eg >> 16) | (eg << 8);
-          } else if (!push) {
-            w[3 * i] = al | (w[3 * i] & 0xFF000000u);
-            w[3 * i + 2] = (w[3 * i + 2] & 0xFFu) | (eg << 8);
-          } else {
-            uint32_t w1 = w[3 * i + 1], w2 = w[3 * i + 2];
-            uint32_t b6 = (w1 >> 16) & 0xFF, b7 = (w1 >> 24) & 0xFF;
-            w[3 * i] = al | (b6 << 24);          /* old bytes 6..11 -> 3..8 ; new ego -> 9..11 */
-            w[3 * i + 1] = b7 | (w2 << 8);
-            w[3 * i + 2] = (w2 >> 24) | (eg << 8);
-          }
-        }
-        __stcs(ptr, make_uint4(w[0], w[1], w[2], w[3]));
-        __stcs(ptr + 1, make_uint4(w[4], w[5], w[6], w[7]));
-        __stcs(ptr + 2, make_uint4(w[8], w[9], w[10], w[11]));
-      } else if (MODE == MG_OBS_LORESCHW4E) {
-        /* [B, 12, R, R]: plane c of frame f is channel 3f + c; 4 pixels = one u32 per plane */
-        uint8_t* base = obs + (size_t)env * 12 * frame_px + (size_t)Y * res_out + X0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          uint32_t nw = ((col[0][0] >> (8 * c)) & 0xFF) | (((col[0][1] >> (8 * c)) & 0xFF) << 8) |
-                        (((col[0][2] >> (8 * c)) & 0xFF) << 16) | (((col[0][3] >> (8 * c)) & 0xFF) << 24);
-          uint32_t* p0 = reinterpret_cast<uint32_t*>(base + (size_t)(0 + c) * frame_px);
-          uint32_t* p1 = reinterpret_cast<uint32_t*>(base + (size_t)(3 + c) * frame_px);
-          uint32_t* p2 = reinterpret_cast<uint32_t*>(base + (size_t)(6 + c) * frame_px);
-          uint32_t* p3 = reinterpret_cast<uint32_t*>(base + (size_t)(9 + c) * frame_px);
-          if (fresh) { *p0 = nw; *p1 = nw; *p2 = nw; *p3 = nw; }
-          else if (!push) { *p3 = nw; }
-          else { uint32_t a = *p1, b = *p2, d = *p3; *p0 = a; *p1 = b; *p2 = d; *p3 = nw; }
-        }
-      } else {
-        /* RAW [2, B, R, R, 3]: 4 pixels = 12 bytes = 3 x u32 */
-#pragma unroll
-        for (int v = 0; v < 1; v++) {
-          uint32_t* ptr = reinterpret_cast<uint32_t*>(
-              obs + (size_t)pass * plane_stride + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 3);
-          uint32_t c0 = col[v][0], c1 = col[v][1], c2 = col[v][2], c3 = col[v][3];
-          ptr[0] = c0 | (c1 << 24);
-          ptr[1] = (c1 >> 8) | (c2 << 16);
-          ptr[2] = (c2 >> 16) | (c3 << 8);
-        }
-      }
+      store_group(X0, Y, pre, col);
     }
   }
   __syncthreads(); /* the next pass rebuilds the shared tables */

@@ -25,11 +25,12 @@ for i in range(n):
 e1.record()
 torch.cuda.synchronize()
 lib.mg_raster_prof_read(buf, 0)
-v = np.array(list(buf), dtype=np.float64)[:8] / (n * B)
-names = ['A prefix', 'B verts', 'C prim records', 'D edge eq', 'E0 span init', 'E1 fold', 'F bins', 'shade+store']
+raw = np.array(list(buf), dtype=np.float64) / (n * B)
+v = np.concatenate([raw[:7], raw[8:10], raw[7:8]])
+names = ['A (static now)', 'B verts', 'C prim records', 'D edge eq', 'E0 span init', 'E1 fold', 'F bins', 'G0 tile desc', 'G1 flat tiles', 'G2 busy tiles']
 print(f'{env_id} B={B}: k_raster {e0.elapsed_time(e1)/n:.3f} ms per launch (instrumented)')
 for nm, c in zip(names, v):
     print(f'  {nm:16s} {c:9.0f} cycles/env  {100*c/v.sum():5.1f} %')
 print(f'  total            {v.sum():9.0f} cycles/env')
-c = np.array(list(buf), dtype=np.float64)[8:12] / (n * B)
+c = np.zeros(4)
 print(f'  per env: flat tiles {c[0]:.1f}, non-flat tiles {c[1]:.1f}, prim visits (per 4-px group) {c[2]:.0f} = {c[2]/max(c[1]*16,1):.2f} per group of a non-flat tile')
