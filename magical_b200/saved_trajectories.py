@@ -46,14 +46,94 @@ class _TrajRewriteUnpickler(pickle.Unpickler):
         return super().find_class(module, name)
 
 
-def load_demos(demo_paths, verbose=False):
-    """Yield the demo dictionaries of a sequence of `.pkl.gz` paths."""
+def load_demos(demo_paths, rewrite_traj_cls=True, verbose=False):
+    """Yield the demo dictionaries of a sequence of `.pkl.gz` paths.  With
+    `rewrite_traj_cls` (the default, as in the reference) every historical
+    trajectory class is mapped onto `MAGICALTrajectory`."""
     n_demos = len(demo_paths)
     for d_num, d_path in enumerate(demo_paths, start=1):
         if verbose:
             print(f"Loading '{d_path}' ({d_num}/{n_demos})")
         with gzip.GzipFile(d_path, 'rb') as fp:
-            yield _TrajRewriteUnpickler(fp).load()
+            unpickler = _TrajRewriteUnpickler(fp) if rewrite_traj_cls \
+                else pickle.Unpickler(fp)
+            yield unpickler.load()
+
+
+def splice_in_preproc_name(base_env_name, preproc_name):
+    """'MoveToCorner-Demo-v0' + 'LoResStack' -> 'MoveToCorner-Demo-LoResStack-v0'
+    (reference saved_trajectories.py:53-62); the preprocessor must exist."""
+    from magical_b200 import benchmarks
+    assert preproc_name in benchmarks.DEFAULT_PREPROC_ENTRY_POINT_WRAPPERS, \
+        f"no preprocessor named '{preproc_name}', options are " \
+        f"{', '.join(benchmarks.DEFAULT_PREPROC_ENTRY_POINT_WRAPPERS)}"
+    return benchmarks.update_magical_env_name(base_env_name,
+                                              preproc=preproc_name)
+
+
+def area_mean_4x4(frames):
+    """cv2.resize(..., INTER_AREA) for an exact 4x reduction: the mean of each
+    4x4 block per channel, rounded half to even (what the LoRes preprocessors
+    apply, benchmarks/__init__.py:159-169, 234).  frames: u8 [..., H, W, C]
+    with H, W multiples of 4."""
+    frames = np.asarray(frames)
+    *lead, h, w, c = frames.shape
+    s = frames.reshape(*lead, h // 4, 4, w // 4, 4, c).astype(np.uint32).sum(
+        axis=(-4, -2))
+    return ((s + 7 + ((s >> 4) & 1)) >> 4).astype(np.uint8)
+
+
+def _stack_last(frames, depth):
+    """[T, H, W, C] -> [T, H, W, depth * C]: at time t the `depth` most recent
+    frames, oldest first, the first frame repeated at the start (the deque of
+    FlattenFrameStack / EagerDictFrameStack, benchmarks/__init__.py:46-136)."""
+    frames = np.asarray(frames)
+    padded = np.concatenate([np.repeat(frames[:1], depth - 1, axis=0), frames])
+    return np.concatenate([padded[k:k + len(frames)] for k in range(depth)],
+                          axis=-1)
+
+
+def preprocess_demos_with_wrapper(trajectories, orig_env_name,
+                                  preproc_name=None, wrapper=None):
+    """Re-preprocess recorded raw trajectories (dict observations with the
+    full-resolution 'allo' and 'ego' views, one more observation than actions)
+    with one of the built-in LoRes pipelines; returns trajectories of the same
+    type whose `obs` is what the `<env>-<preproc>-v0` id would have returned
+    during that episode (reference saved_trajectories.py:90-160, which replays
+    the recorded frames through the gym wrappers; here the same arithmetic is
+    applied to the whole episode at once).  Custom `wrapper` callables are a
+    gym-wrapper mechanism and are not supported."""
+    from magical_b200 import benchmarks
+    if wrapper is not None:
+        raise NotImplementedError(
+            'only the built-in preprocessors (preproc_name=...) are supported')
+    assert preproc_name in benchmarks.DEFAULT_PREPROC_ENTRY_POINT_WRAPPERS, \
+        preproc_name
+    benchmarks.register_envs()
+    if orig_env_name not in benchmarks.ENV_SPECS:
+        raise KeyError(f"no registered MAGICAL env with id '{orig_env_name}'")
+    out = []
+    for traj in trajectories:
+        if isinstance(traj.obs, dict):
+            allo, ego = np.asarray(traj.obs['allo']), np.asarray(traj.obs['ego'])
+        else:   # a sequence of per-step dicts
+            allo = np.stack([o['allo'] for o in traj.obs])
+            ego = np.stack([o['ego'] for o in traj.obs])
+        lo_a, lo_e = area_mean_4x4(allo), area_mean_4x4(ego)
+        if preproc_name == 'LoResStack':
+            obs = collections.OrderedDict([('allo', _stack_last(lo_a, 4)),
+                                           ('ego', _stack_last(lo_e, 4))])
+        elif preproc_name == 'LoRes4A':
+            obs = _stack_last(lo_a, 4)
+        elif preproc_name == 'LoRes3EA':
+            obs = np.concatenate([lo_a, _stack_last(lo_e, 3)], axis=-1)
+        else:
+            obs = _stack_last(lo_e, 4)
+            if preproc_name == 'LoResCHW4E':
+                obs = np.moveaxis(obs, -1, 1)
+        out.append(type(traj)(acts=np.asarray(traj.acts), obs=obs,
+                              rews=np.asarray(traj.rews), infos=traj.infos))
+    return out
 
 
 def save_demo(path, env_name, trajectory, score):

@@ -40,6 +40,100 @@ def test_round_trip_and_class_rewrite(tmp_path):
         assert np.array_equal(d['trajectory'].acts, np.arange(5))
 
 
+def _oracle_demo(env_name, actions, with_obs=False):
+    """A demonstration recorded by the CPU ORACLE: scripted actions, the oracle's physics and score
+    function, and (with_obs) its brute-force 384x384 renders of both views, in the reference's
+    trajectory layout (one more observation than actions)."""
+    import magical_b200 as magical
+    from oracle_lib import OracleEnv
+    task, spec = magical.make_task(env_name)
+    orc = OracleEnv(task.build_scene(), det_sincos=True)
+    obs = {'allo': [], 'ego': []}
+
+    def snap():
+        if with_obs:
+            obs['allo'].append(orc.render_view(0, 384))
+            obs['ego'].append(orc.render_view(1, 384))
+    snap()
+    for a in actions:
+        orc.step(int(a))
+        snap()
+    score = float(np.float32(orc.score()))
+    traj = st.MAGICALTrajectory(
+        acts=np.asarray(actions, dtype=np.int64),
+        obs={k: np.stack(v) for k, v in obs.items()} if with_obs else {},
+        rews=np.zeros(len(actions)), infos=None)
+    orc.close()
+    return traj, score
+
+
+def _pushy(rng, n):
+    return [int(rng.randint(18)) if rng.rand() < 0.5 else int(rng.choice([1, 4, 7, 10, 13, 16]))
+            for _ in range(n)]
+
+
+def test_preprocess_demos_matches_oracle_downsample():
+    """area_mean_4x4 / preprocess_demos_with_wrapper against the oracle's INTER_AREA statement (itself
+    pinned to real cv2 in test_oracle_golden.py) on oracle-rendered frames, all five layouts."""
+    from oracle_lib import downsample4
+    rng = np.random.RandomState(4)
+    traj, _ = _oracle_demo('MoveToCorner-Demo-v0', _pushy(rng, 6), with_obs=True)
+    lo = {k: np.stack([downsample4(f) for f in traj.obs[k]]) for k in ('allo', 'ego')}
+    assert np.array_equal(st.area_mean_4x4(traj.obs['ego']), lo['ego'])
+
+    def stack(frames, depth, t):
+        idx = [max(t - k, 0) for k in range(depth - 1, -1, -1)]
+        return np.concatenate([frames[i] for i in idx], axis=-1)
+
+    outs = {p: st.preprocess_demos_with_wrapper([traj], 'MoveToCorner-Demo-v0', preproc_name=p)[0]
+            for p in ('LoRes4E', 'LoRes4A', 'LoRes3EA', 'LoResStack', 'LoResCHW4E')}
+    for t in range(len(traj.acts) + 1):
+        assert np.array_equal(outs['LoRes4E'].obs[t], stack(lo['ego'], 4, t))
+        assert np.array_equal(outs['LoRes4A'].obs[t], stack(lo['allo'], 4, t))
+        assert np.array_equal(outs['LoRes3EA'].obs[t],
+                              np.concatenate([lo['allo'][t], stack(lo['ego'], 3, t)], axis=-1))
+        assert np.array_equal(outs['LoResStack'].obs['allo'][t], stack(lo['allo'], 4, t))
+        assert np.array_equal(outs['LoResCHW4E'].obs[t], np.moveaxis(stack(lo['ego'], 4, t), -1, 0))
+    assert outs['LoRes4E'].obs.shape == (7, 96, 96, 12) and outs['LoResCHW4E'].obs.shape == (7, 12, 96, 96)
+    assert st.splice_in_preproc_name('MoveToCorner-Demo-v0', 'LoResStack') == 'MoveToCorner-Demo-LoResStack-v0'
+    with pytest.raises(AssertionError):
+        st.splice_in_preproc_name('MoveToCorner-Demo-v0', 'NoSuchPreproc')
+
+
+@pytest.mark.gpu
+def test_replay_of_oracle_recorded_demos(built, tmp_path):
+    """demonstrations recorded by the ORACLE (its physics, its score functions),
+    written in the reference's file format, replayed through the GPU engine in one batch per env id:
+    the replayed score equals the recorded one for every demo, and the observations the GPU env returns
+    during the replay equal the recorded raw frames pushed through preprocess_demos_with_wrapper."""
+    import torch
+    import magical_b200 as magical
+    rng = np.random.RandomState(12)
+    specs = [('MoveToRegion-Demo-v0', 40), ('ClusterColour-Demo-v0', 150), ('MoveToCorner-Demo-v0', 80),
+             ('MatchRegions-Demo-v0', 110), ('MoveToRegion-Demo-v0', 25), ('FixColour-Demo-v0', 60),
+             ('FindDupe-Demo-v0', 100), ('MakeLine-Demo-v0', 140), ('ClusterShape-Demo-v0', 200)]
+    paths, demos = [], []
+    for n, (env_name, length) in enumerate(specs):
+        traj, score = _oracle_demo(env_name, _pushy(rng, length), with_obs=(n == 2))
+        demos.append((env_name, traj, score))
+        paths.append(str(tmp_path / f'demo-{n}.pkl.gz'))
+        st.save_demo(paths[-1], env_name, traj, score)
+    out = st.replay_demos(st.load_demos(paths))
+    assert [o['n_actions'] for o in out] == [l for _, l in specs]
+    for o in out:
+        assert np.float32(o['replayed_score']) == np.float32(o['recorded_score']), o
+    assert len({o['recorded_score'] for o in out}) >= 3      # the scores are not all trivially equal
+    # observations: recorded raw frames -> LoRes4E == what the GPU env shows on the same actions
+    env_name, traj, _ = demos[2]
+    want = st.preprocess_demos_with_wrapper([traj], env_name, preproc_name='LoRes4E')[0].obs
+    venv = magical.make_vec(st.splice_in_preproc_name(env_name, 'LoRes4E'), 1, auto_reset=False)
+    assert np.array_equal(venv.reset()[0].cpu().numpy(), want[0])
+    for t, a in enumerate(traj.acts[:30]):
+        obs = venv.step(torch.tensor([int(a)], dtype=torch.int32, device='cuda'))[0]
+        assert np.array_equal(obs[0].cpu().numpy(), want[t + 1]), t
+    venv.close()
+
+
 @pytest.mark.gpu
 def test_replay_reproduces_recorded_scores(built, tmp_path):
     """Self-recorded demonstrations (random actions on the GPU engine, written
