@@ -19,9 +19,11 @@ without the observation gather (--no-records skips them).
 
   value : env-steps/s, whole job, actions already resident in HBM, CUDA events on the launching stream,
           median of 3 repeats of K steps, max over ranks.  At N>1 every rank ends each step with the global
-          observation / reward / done / score batch (ShardedVecEnv, gather_obs='newest', pipelined: the
-          gather + stack push of step t overlap the physics of step t+1; everything is complete before the
-          closing event).
+          observation / reward / done / score batch (ShardedVecEnv, gather_obs='newest': flag barrier, then
+          k_stack_push_p2p reads the other ranks' newest frames over NVLink and rebuilds their stacks).  The
+          exchange is NOT overlapped with the next step's physics by default: measured on B200, the
+          bandwidth-saturating stack rebuild slows the latency-bound physics kernel by more than its own
+          duration when they run together (profiles/r02_bench_log.md); --pipeline turns the overlap on.
   e2e   : the same metric through the public API with HOST action buffers, closed loop: every step copies the
           (global) actions H2D from pinned memory, waits for the gather, and reads reward/done/eval_score of
           the global batch back D2H before the next step.  The observation stays in the device tensor the
@@ -245,7 +247,7 @@ class Runner:
                                     alloc_obs=not sharded_obs)
 
         self.env = mdist.ShardedVecEnv(make_local, total, rank, world, gather_obs=self.gather_obs,
-                                       pipeline=True, transport=args.transport)
+                                       pipeline=args.pipeline, transport=args.transport)
         self.venv = self.env.local
         self.views = 2 if self.venv.preproc == 'LoResStack' else 1
         self.env.reset()
@@ -419,8 +421,8 @@ class Runner:
             par += '; all-gather of reward/done/score'
             if self.gather_obs == 'newest':
                 par += (f' + obs (transport {self.env.transport}: newest frame of every env over NVLink, '
-                        'k_stack_push rebuilds the global stacks on every rank; exchange + push on a side stream, '
-                        'overlapped with the next step\'s physics)')
+                        'k_stack_push rebuilds the global stacks on every rank'
+                        + ("; exchange + push overlap the next step's physics" if self.args.pipeline else '') + ')')
         return {
             'workload': f'{self.label}: {self.total} envs global, {per} per GPU, random actions, auto-reset',
             'env_id': self.env_id if isinstance(self.env_id, str) else self.env_id,
@@ -517,6 +519,8 @@ def main():
     ap.add_argument('--no-gather-obs', action='store_true',
                     help='N>1: gather only reward/done/score (round-1 behaviour)')
     ap.add_argument('--no-records', action='store_true')
+    ap.add_argument('--pipeline', action='store_true',
+                    help='N>1: let the exchange + stack rebuild of step t overlap the physics of step t+1')
     ap.add_argument('--transport', default='auto', choices=['auto', 'p2p', 'nccl'],
                     help='N>1 observation gather: NVLink peer memory (default) or ncclAllGather')
     ap.add_argument('--prelude', type=int, default=-1,
