@@ -243,8 +243,11 @@ class Runner:
                 return magical.make_vec_mixed(env_id, n, device=self.local_rank, alloc_obs=not sharded_obs,
                                               first_env=start, total=total)
             # fixed seed: the randomised variants sample their scene pool from it (reproducible workload)
+            # randomised (Test*) variants: the pool holds structure TEMPLATES and every reset samples a fresh
+            # layout on the device, as the reference re-randomises on every reset
             return magical.make_vec(env_id, n, device=self.local_rank, auto_reset=True, seed=1234 + rank,
-                                    alloc_obs=not sharded_obs)
+                                    alloc_obs=not sharded_obs,
+                                    device_sampling=magical.EnvName(env_id).is_test)
 
         self.env = mdist.ShardedVecEnv(make_local, total, rank, world, gather_obs=self.gather_obs,
                                        pipeline=args.pipeline, transport=args.transport)
@@ -427,6 +430,9 @@ class Runner:
             'workload': f'{self.label}: {self.total} envs global, {per} per GPU, random actions, auto-reset',
             'env_id': self.env_id if isinstance(self.env_id, str) else self.env_id,
             'batch_per_gpu': per, 'global_batch': self.total, 'parallelism': par,
+            'resets': ('device-side rejection sampling of goal sizes and poses at every reset (k_sample_layouts), '
+                       f'{self.venv.n_scenes} host-built structure templates') if self.venv.device_sampling
+            else 'deterministic Demo layout',
             'episode_phase': (f'uniform over the {self.prelude_steps}-step episode (untimed prelude of '
                               f'{self.prelude_steps} steps with staggered resets)')
             if self.prelude_steps > 0 else 'all envs at episode start',

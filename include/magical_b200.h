@@ -204,8 +204,42 @@ typedef struct {
                            reference re-randomises the layout on every reset, base_env.py:177-234) */
   int32_t keep_scene;   /* 1: auto-reset restarts an env on the scene it is bound to (e.g. a mixed-task batch)
                            instead of drawing a new pool entry */
-  int32_t reserved_[7];
+  int32_t device_sampling; /* 1: the n_scenes scenes are TEMPLATES (structure: shape types, colours, counts, dynamics);
+                           every reset draws a template and rejection-samples fresh goal sizes and poses for it ON
+                           THE DEVICE into a scene slot owned by the environment (mg_set_placement) */
+  int32_t reserved_[6];
 } mg_config_t;
+
+/* ---- placement program of one template: what the task's on_reset() asks the reference's rejection sampler
+ * to randomise (pm_randomise_all_poses / randomise_hw, magical/geom.py:116-359), recorded by the host while it
+ * builds the template.  Entities are placed in list order, each avoiding the arena walls, every entity that is
+ * not on the list, and the list entries placed before it (goal sensors count as obstacles). ---- */
+#define MG_MAX_PLACE_ENTS 16
+#define MG_MAX_PLACE_BODIES 6
+typedef struct {
+  int32_t kind;      /* 0: bodies that move rigidly together (robot: body, control, eyes, fingers); 1: goal region */
+  int32_t goal;      /* kind 1: goal index */
+  int32_t n_bodies;  /* kind 0 */
+  int32_t n_groups;  /* kind 0: collision groups carrying the entity's shapes */
+  int32_t bodies[MG_MAX_PLACE_BODIES]; /* main body first */
+  int32_t groups[4];
+  int32_t rand_pos, rand_rot;
+  double pos_limit;  /* l-infinity bound around orig (< 0: anywhere in the arena) */
+  double rot_limit;  /* bound around orig[2] (< 0: [-pi, pi]) */
+  double orig[3];    /* main body pose before randomisation; goal: TOP-LEFT corner x, y (entities.py:790-798) */
+} mg_place_ent_t;
+typedef struct {
+  int32_t goal, pad_;
+  double min_side, max_side, cur_h, cur_w;
+  double linf;       /* bound around (cur_h, cur_w); < 0: none */
+} mg_place_hw_t;
+typedef struct {
+  int32_t n_ents, n_hw;
+  int32_t goal_prims[MG_MAX_GOALS][2]; /* fill and border primitive of every goal (world-space rectangles) */
+  double arena[4];   /* l, r, b, t */
+  mg_place_ent_t ents[MG_MAX_PLACE_ENTS];
+  mg_place_hw_t hw[MG_MAX_GOALS];
+} mg_placement_t;
 
 /* One environment's COMPLETE simulator state in host-readable form: what mg_get_state returns and
  * mg_set_state restores (checkpoint / resume, parity tests).  Everything Chipmunk carries from one
@@ -291,6 +325,20 @@ int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* sce
 int mg_update_scenes(mg_handle* h, int32_t first, int32_t n, const mg_scene_t* scenes);
 int mg_set_draw_range(mg_handle* h, int32_t first, int32_t n);
 
+/* Device-side reset randomisation (cfg->device_sampling; replaces geom.py:116-359 at reset time).
+ * mg_set_placement uploads the placement programs of templates [first, first + n) (required before the first
+ * reset; again after mg_update_scenes streams new templates).  With it, every reset -- mg_reset and the
+ * auto-reset inside mg_step -- draws a template, samples goal sizes and poses with the reference's procedure
+ * (uniform draws, same try / retry limits, same obstacle rules; Philox streams keyed by reset_seed, env and the
+ * env's reset count: same distribution as the reference, not the same numpy stream) and plays the result from a
+ * scene slot of its own.  mg_get_env_scene returns the scene an environment is playing (what the oracle needs to
+ * reproduce the episode); mg_sampler_failures counts resets that fell back to the template's own host-sampled
+ * poses because no placement was found within the reference's limits. */
+int64_t mg_sizeof_placement(void);
+int mg_set_placement(mg_handle* h, int32_t first, int32_t n, const mg_placement_t* programs);
+int mg_get_env_scene(mg_handle* h, int32_t env, mg_scene_t* out);
+int mg_sampler_failures(mg_handle* h, int64_t* out);
+
 /* One env-step for the whole batch: Robot.set_action + 10 x (Robot.update + Space.step)
  * + episode bookkeeping + score + render + stack (base_env.py:255-292).
  * actions: DEVICE int32[batch] in [0,18).  reward/done/score: DEVICE, caller-owned, [batch]
@@ -322,6 +370,9 @@ int mg_get_state(mg_handle* h, int32_t env, mg_state_t* out);
  * continues bit for bit.  The observation stack is not touched (call mg_render for a frame of the new state).
  * SURVEY 8(b) `mg_set_state`; no reference counterpart (pymunk spaces are pickled whole). */
 int mg_set_state(mg_handle* h, int32_t env, const mg_state_t* in);
+/* Poses of every body of every environment in one copy: out_host is HOST double [batch][MG_MAX_BODIES][4]
+ * (x, y, angle, 0).  Synchronises the stream. */
+int mg_get_poses(mg_handle* h, double* out_host);
 int mg_set_pose(mg_handle* h, int32_t env, int32_t body, double x, double y, double angle);
 
 /* Number of kernels launched by this handle since creation (bench bookkeeping). */

@@ -24,6 +24,8 @@ ABI_SYMBOLS = [
     'mg_comm_create', 'mg_comm_export', 'mg_comm_connect', 'mg_comm_scalar_ptr',
     'mg_comm_frame_ptr', 'mg_comm_barrier', 'mg_comm_gather_scalars',
     'mg_comm_stack_push', 'mg_comm_error', 'mg_comm_destroy',
+    'mg_sizeof_placement', 'mg_set_placement', 'mg_get_env_scene',
+    'mg_sampler_failures', 'mg_get_poses',
 ]
 COMM_HANDLE_BYTES = 64
 
@@ -68,6 +70,11 @@ def load():
     L.mg_newest_nbytes.argtypes = [vp]
     L.mg_bind_newest.argtypes = [vp, vp, i64]
     L.mg_stack_push.argtypes = [vp, vp, vp, i64, i64, i32, i64, i32, vp]
+    L.mg_sizeof_placement.restype = i64
+    L.mg_set_placement.argtypes = [vp, i32, i32, vp]
+    L.mg_get_env_scene.argtypes = [vp, i32, vp]
+    L.mg_sampler_failures.argtypes = [vp, vp]
+    L.mg_get_poses.argtypes = [vp, vp]
     L.mg_comm_create.argtypes = [i32, i32, i32, i64, i64, ctypes.POINTER(vp)]
     L.mg_comm_export.argtypes = [vp, vp]
     L.mg_comm_connect.argtypes = [vp, vp]
@@ -92,6 +99,10 @@ def load():
     L.mg_overflow_count.argtypes = [vp, vp]
     if L.mg_version() != sc.ABI_VERSION:
         raise NativeError("ABI version mismatch between Python and library")
+    if L.mg_sizeof_placement() != sc.placement_dt.itemsize:
+        raise NativeError(
+            f"struct layout mismatch: mg_placement_t is {L.mg_sizeof_placement()} "
+            f"bytes in C, {sc.placement_dt.itemsize} in numpy")
     if L.mg_sizeof_scene() != sc.scene_dt.itemsize \
             or L.mg_sizeof_state() != sc.state_dt.itemsize:
         raise NativeError(

@@ -93,14 +93,70 @@ class BaseEnv(abc.ABC):
         for entity in entities:
             if isinstance(entity, en.Robot):
                 self._robot = entity
+            if isinstance(entity, en.GoalRegion):
+                self._goal_entities.append(entity)
             self._entities.append(entity)
             self._builder.entities.append(entity)
             entity.setup(self._builder)
+
+    def build_template(self):
+        """A compiled scene plus its PLACEMENT PROGRAM: what `on_reset()` asked
+        the rejection sampler to randomise (goal sizes, entity poses with
+        their limits), recorded while the scene is built, so that the device
+        can re-sample sizes and poses for this structure at every reset
+        (`mg_set_placement`, csrc/mg_sample.cu).  Raises NotImplementedError
+        for tasks whose reset uses sampler features the device kernel does not
+        implement (FindDupe / FixColour: `ignore_ents`, follow-up placements
+        relative to another entity)."""
+        self._placement_log = {'hw': [], 'ents': None, 'unsupported': None}
+        try:
+            record = self.build_scene()
+            log = self._placement_log
+        finally:
+            self._placement_log = None
+        if log['unsupported']:
+            raise NotImplementedError(
+                f'{type(self).__name__}: device-side layout sampling does not '
+                f"cover this task's reset ({log['unsupported']})")
+        prog = np.zeros((), dtype=sc.placement_dt)
+        prog['arena'] = self.ARENA_BOUNDS_LRBT
+        prog['goal_prims'] = -1
+        n_goals = int(record['n_goals'])
+        for ent in self._goal_entities:
+            prog['goal_prims'][ent.goal_index] = ent.prim_ids
+        assert len(log['hw']) <= n_goals, 'more size draws than goal regions'
+        prog['n_hw'] = len(log['hw'])
+        for k, (mn, mx, cur, linf) in enumerate(log['hw']):
+            # the k-th (h, w) draw sizes the k-th goal region created
+            h = prog['hw'][k]
+            h['goal'] = k
+            h['min_side'], h['max_side'] = mn, mx
+            h['cur_h'], h['cur_w'] = cur if cur is not None else (0.0, 0.0)
+            h['linf'] = -1.0 if linf is None else linf
+        ents = log['ents'] or []
+        assert len(ents) <= sc.MAX_PLACE_ENTS
+        prog['n_ents'] = len(ents)
+        for k, e in enumerate(ents):
+            pe = prog['ents'][k]
+            pe['rand_pos'], pe['rand_rot'] = int(e['rand_pos']), int(e['rand_rot'])
+            pe['pos_limit'] = -1.0 if e['pos_limit'] is None else e['pos_limit']
+            pe['rot_limit'] = -1.0 if e['rot_limit'] is None else e['rot_limit']
+            pe['orig'] = e['orig']
+            if e['goal'] is not None:
+                pe['kind'], pe['goal'] = 1, e['goal']
+            else:
+                assert len(e['bodies']) <= sc.MAX_PLACE_BODIES and len(e['groups']) <= 4
+                pe['kind'] = 0
+                pe['n_bodies'], pe['n_groups'] = len(e['bodies']), len(e['groups'])
+                pe['bodies'][:len(e['bodies'])] = e['bodies']
+                pe['groups'][:len(e['groups'])] = e['groups']
+        return record, prog
 
     def build_scene(self):
         """The scene-construction half of reference `reset()`
         (base_env.py:177-223): returns one compiled scene record."""
         self._entities = []
+        self._goal_entities = []
         self._robot = None
         if self.rand_dynamics:
             phys_vars = PhysicsVariables.sample(self.rng)
@@ -139,17 +195,56 @@ class BaseEnv(abc.ABC):
             current_hw = np.asarray(current_hw, dtype='float64')
             minima = np.maximum(minima, current_hw - linf_bound)
             maxima = np.minimum(maxima, current_hw + linf_bound)
+        log = getattr(self, '_placement_log', None)
+        if log is not None:
+            log['hw'].append((float(min_side), float(max_side),
+                              None if current_hw is None
+                              else (float(current_hw[0]), float(current_hw[1])),
+                              None if linf_bound is None else float(linf_bound)))
         h, w = self.rng.uniform(minima, maxima)
         return float(h), float(w)
 
     def randomise_all_poses(self, entities, **kwargs):
         from magical_b200 import placement
+        log = getattr(self, '_placement_log', None)
+        if log is not None:
+            self._log_placement(log, list(entities), **kwargs)
         placement.randomise_all_poses(self._builder, entities,
                                       self.ARENA_BOUNDS_LRBT, self.rng,
                                       **kwargs)
 
+    def _log_placement(self, log, entities, rand_pos=True, rand_rot=True,
+                       rel_pos_linf_limits=None, rel_rot_limits=None,
+                       ignore_ents=None, max_retries=10):
+        from magical_b200 import placement
+        if log['ents'] is not None:
+            log['unsupported'] = 'more than one randomise_all_poses call'
+            return
+        if ignore_ents:
+            log['unsupported'] = 'ignore_ents'
+            return
+        n = len(entities)
+        lists = [placement._listify(v, n) for v in
+                 (rand_pos, rand_rot, rel_pos_linf_limits, rel_rot_limits)]
+        out = []
+        for ent, rp, rr, pl, rl in zip(entities, *lists):
+            if isinstance(ent, en.GoalRegion):
+                out.append(dict(goal=ent.goal_index, bodies=[], groups=[],
+                                orig=(ent.x, ent.y, 0.0), rand_pos=rp,
+                                rand_rot=rr, pos_limit=pl, rot_limit=rl))
+            else:
+                (pos, ang) = placement.entity_pose(self._builder, ent)
+                out.append(dict(goal=None, bodies=list(ent.body_ids),
+                                groups=list(ent.cgroup_ids),
+                                orig=(pos[0], pos[1], ang), rand_pos=rp,
+                                rand_rot=rr, pos_limit=pl, rot_limit=rl))
+        log['ents'] = out
+
     def randomise_pose(self, entity, **kwargs):
         from magical_b200 import placement
+        log = getattr(self, '_placement_log', None)
+        if log is not None:
+            log['unsupported'] = 'a separate randomise_pose call'
         placement.randomise_pose(self._builder, entity,
                                  self.ARENA_BOUNDS_LRBT, self.rng, **kwargs)
 

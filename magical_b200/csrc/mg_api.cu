@@ -31,10 +31,13 @@ cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, c
 size_t mg_tpe_smem_bytes(const TpeLayout* L);
 size_t mg_tpe_spill_doubles_per_env(const TpeLayout* L);
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
-                             int draw_first, int draw_count, uint32_t reset_seed, float* reward, uint8_t* done,
-                             float* score, unsigned long long* overflow_count, cudaStream_t stream);
+                             int draw_first, int draw_count, uint32_t reset_seed, int sample_mode, float* reward,
+                             uint8_t* done, float* score, unsigned long long* overflow_count, cudaStream_t stream);
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
-                            const int32_t* scene_ids, int first_time, cudaStream_t stream);
+                            const int32_t* scene_ids, int first_time, int sample_mode, cudaStream_t stream);
+cudaError_t mg_launch_sample_layouts(EnvState* states, DeviceScene* scenes, const mg_placement_t* programs,
+                                     int n_templates, int batch, uint32_t seed, unsigned long long* failures,
+                                     cudaStream_t stream);
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, uint8_t* newest,
                              size_t plane_stride, int batch, int res_out, int ecap, int scap, int rcap, int only_fresh,
                              int push, int env0, int count, cudaStream_t stream);
@@ -65,6 +68,10 @@ struct mg_handle {
   double* d_spill;      /* its contact spill area */
   uint32_t* d_scratch;  /* its per-environment work-item / separation-cache records (scratch_global layout) */
   unsigned long long* d_overflow; /* environments x episodes that hit a physics capacity limit (k_finish counts) */
+  /* device-side layout sampling (cfg.device_sampling): d_scenes = [n_scenes templates | batch slots] */
+  mg_placement_t* d_programs;
+  unsigned long long* d_failures;
+  int programs_set;
   /* mg_step software pipeline: the batch is cut into chunks whose physics and raster kernels run on two
    * internal streams, staggered so that the raster of chunk c overlaps the physics of chunk c + 1 (the
    * physics is latency-bound at ~13 % issue utilisation, the raster issue-bound: they share SMs well) */
@@ -182,6 +189,9 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
     int edges = 0, rprims = 0, rows = 0;
     const char* bad = scene_raster_needs(scenes[i], res_full, &edges, &rprims, &rows);
     if (bad) return fail(MG_E_INVALID, "mg_create: %s", bad);
+    /* device-side sampling re-draws goal sizes (up to 0.8 a side, base_env.py:RAND_GOAL_MAX_SIZE): room for
+     * the largest fill (its diagonal) and four border segments per goal, whatever the template's size is */
+    if (cfg->device_sampling) rows += 900 * ss * scenes[i].n_goals / 4;
     if (edges > ecap) ecap = edges;
     if (rows > scap) scap = rows;
     if (rprims > rcap) rcap = rprims;
@@ -258,7 +268,13 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   }
   cudaError_t e;
   if ((e = cudaMalloc(&h->d_states, sizeof(EnvState) * (size_t)cfg->batch)) != cudaSuccess ||
-      (e = cudaMalloc(&h->d_scenes, sizeof(DeviceScene) * (size_t)cfg->n_scenes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_scenes, sizeof(DeviceScene) * ((size_t)cfg->n_scenes +
+                                                             (cfg->device_sampling ? (size_t)cfg->batch : 0)))) != cudaSuccess ||
+      (cfg->device_sampling &&
+       ((e = cudaMalloc(&h->d_programs, sizeof(mg_placement_t) * (size_t)cfg->n_scenes)) != cudaSuccess ||
+        (e = cudaMemset(h->d_programs, 0, sizeof(mg_placement_t) * (size_t)cfg->n_scenes)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_failures, sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(h->d_failures, 0, sizeof(unsigned long long))) != cudaSuccess)) ||
       (e = cudaMalloc(&h->d_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_scene_ids, sizeof(int32_t) * (size_t)cfg->batch)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_overflow, sizeof(unsigned long long))) != cudaSuccess ||
@@ -307,7 +323,7 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
       units[offs[t] + k][1] = sin(ang);
     }
   if ((e = mg_raster_upload_units(&units[0][0])) != cudaSuccess ||
-      (e = mg_launch_reset(h->d_states, h->d_scenes, cfg->batch, nullptr, nullptr, 1, h->stream)) != cudaSuccess ||
+      (e = mg_launch_reset(h->d_states, h->d_scenes, cfg->batch, nullptr, nullptr, 1, 0, h->stream)) != cudaSuccess ||
       (e = cudaStreamSynchronize(h->stream)) != cudaSuccess) {
     mg_destroy(h);
     return fail(MG_E_CUDA, "mg_create: init: %s", cudaGetErrorString(e));
@@ -328,6 +344,8 @@ int mg_destroy(mg_handle* h) {
   cudaFree(h->d_spill);
   cudaFree(h->d_scratch);
   cudaFree(h->d_overflow);
+  cudaFree(h->d_programs);
+  cudaFree(h->d_failures);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   for (int i = 0; i < 2; i++) {
     if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
@@ -420,9 +438,16 @@ int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* sce
         return fail(MG_E_INVALID, "mg_reset: scene id out of range%s", "");
     CUDA_TRY(cudaMemcpyAsync(h->d_scene_ids, scene_ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   }
+  if (h->cfg.device_sampling && (!scene_ids || !h->programs_set))
+    return fail(MG_E_STATE, "mg_reset: device-side layout sampling needs template ids (scene_ids) and mg_set_placement first%s", "");
   CUDA_TRY(mg_launch_reset(h->d_states, h->d_scenes, n, env_ids ? h->d_ids : nullptr,
-                           scene_ids ? h->d_scene_ids : nullptr, 0, h->stream));
+                           scene_ids ? h->d_scene_ids : nullptr, 0, h->cfg.device_sampling, h->stream));
   h->launches++;
+  if (h->cfg.device_sampling) {
+    CUDA_TRY(mg_launch_sample_layouts(h->d_states, h->d_scenes, h->d_programs, h->cfg.n_scenes, h->cfg.batch,
+                                      (uint32_t)h->cfg.reset_seed, h->d_failures, h->stream));
+    h->launches++;
+  }
   /* the host arrays may be reused by the caller as soon as we return */
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (h->obs) return do_raster(h, 1, 1);
@@ -439,8 +464,15 @@ static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_de
     CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads,
                                h->stream));
   CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, h->cfg.auto_reset, 0, h->draw_first, h->draw_count,
-                            (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->d_overflow, h->stream));
+                            (uint32_t)h->cfg.reset_seed, h->cfg.device_sampling, reward_dev, done_dev, score_dev,
+                            h->d_overflow, h->stream));
   h->launches += 2;
+  if (h->cfg.device_sampling && h->cfg.auto_reset) {
+    /* environments that finished an episode get a freshly sampled layout before the render */
+    CUDA_TRY(mg_launch_sample_layouts(h->d_states, h->d_scenes, h->d_programs, h->cfg.n_scenes, h->cfg.batch,
+                                      (uint32_t)h->cfg.reset_seed, h->d_failures, h->stream));
+    h->launches++;
+  }
   return MG_OK;
 }
 
@@ -466,7 +498,7 @@ static int step_pipelined(mg_handle* h, const int32_t* actions_dev, float* rewar
                                    st));
     CUDA_TRY(cudaEventRecord(h->ev_phys[c & 1], st));
     CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, env0, count, h->cfg.auto_reset, 0, h->draw_first, h->draw_count,
-                              (uint32_t)h->cfg.reset_seed, reward_dev, done_dev, score_dev, h->d_overflow, st));
+                              (uint32_t)h->cfg.reset_seed, 0, reward_dev, done_dev, score_dev, h->d_overflow, st));
     CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->newest, (size_t)h->plane_stride, B,
                               h->res_out, h->ecap, h->scap, h->rcap, 0, 1, env0, count, st));
     h->launches += 3;
@@ -481,7 +513,7 @@ static int step_pipelined(mg_handle* h, const int32_t* actions_dev, float* rewar
 int mg_step(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
   if (!h) return fail(MG_E_INVALID, "mg_step: null handle%s", "");
   if (!h->obs) return fail(MG_E_STATE, "mg_step: no observation buffer bound (call mg_bind_obs first)%s", "");
-  if (h->n_chunks > 1) return step_pipelined(h, actions_dev, reward_dev, done_dev, score_dev);
+  if (h->n_chunks > 1 && !h->cfg.device_sampling) return step_pipelined(h, actions_dev, reward_dev, done_dev, score_dev);
   int rc = do_physics(h, actions_dev, reward_dev, done_dev, score_dev);
   if (rc != MG_OK) return rc;
   return do_raster(h, 0, 1);
@@ -507,7 +539,8 @@ int mg_render(mg_handle* h) {
 int mg_score(mg_handle* h, float* score_dev) {
   if (!h || !score_dev) return fail(MG_E_INVALID, "mg_score: null argument%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, 0, 1, 0, 1, 0u, nullptr, nullptr, score_dev, nullptr, h->stream));
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, 0, 1, 0, 1, 0u, 0, nullptr, nullptr, score_dev, nullptr,
+                            h->stream));
   h->launches++;
   return MG_OK;
 }
@@ -602,6 +635,73 @@ int mg_update_scenes(mg_handle* h, int32_t first, int32_t n, const mg_scene_t* s
   CUDA_TRY(cudaMemcpyAsync(h->d_scenes + first, host.data(), sizeof(DeviceScene) * (size_t)n, cudaMemcpyHostToDevice,
                            h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return MG_OK;
+}
+
+int64_t mg_sizeof_placement(void) { return (int64_t)sizeof(mg_placement_t); }
+
+int mg_set_placement(mg_handle* h, int32_t first, int32_t n, const mg_placement_t* programs) {
+  if (!h || !programs) return fail(MG_E_INVALID, "mg_set_placement: null argument%s", "");
+  if (!h->cfg.device_sampling) return fail(MG_E_STATE, "mg_set_placement: the handle was not created with device_sampling%s", "");
+  if (first < 0 || n <= 0 || first + n > h->cfg.n_scenes) return fail(MG_E_INVALID, "mg_set_placement: range%s", "");
+  for (int i = 0; i < n; i++) {
+    const mg_placement_t& P = programs[i];
+    if (P.n_ents < 0 || P.n_ents > MG_MAX_PLACE_ENTS || P.n_hw < 0 || P.n_hw > MG_MAX_GOALS)
+      return fail(MG_E_INVALID, "mg_set_placement: bad entity / size-draw count%s", "");
+    for (int k = 0; k < P.n_ents; k++) {
+      const mg_place_ent_t& E = P.ents[k];
+      bool ok = (E.kind == 0 || E.kind == 1);
+      if (E.kind == 1) ok = ok && E.goal >= 0 && E.goal < MG_MAX_GOALS;
+      if (E.kind == 0) {
+        ok = ok && E.n_bodies >= 1 && E.n_bodies <= MG_MAX_PLACE_BODIES && E.n_groups >= 0 && E.n_groups <= 4;
+        for (int j = 0; ok && j < E.n_bodies; j++) ok = E.bodies[j] >= 0 && E.bodies[j] < MG_MAX_BODIES;
+        for (int j = 0; ok && j < E.n_groups; j++) ok = E.groups[j] >= 0 && E.groups[j] < MG_MAX_CGROUPS;
+      }
+      if (!ok || !(E.rand_pos || E.rand_rot)) return fail(MG_E_INVALID, "mg_set_placement: bad entity entry%s", "");
+    }
+    for (int k = 0; k < P.n_hw; k++)
+      if (P.hw[k].goal < 0 || P.hw[k].goal >= MG_MAX_GOALS) return fail(MG_E_INVALID, "mg_set_placement: bad size-draw entry%s", "");
+    for (int g = 0; g < MG_MAX_GOALS; g++)
+      for (int q = 0; q < 2; q++)
+        if (P.goal_prims[g][q] >= MG_MAX_PRIMS) return fail(MG_E_INVALID, "mg_set_placement: bad goal primitive%s", "");
+  }
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpyAsync(h->d_programs + first, programs, sizeof(mg_placement_t) * (size_t)n, cudaMemcpyHostToDevice,
+                           h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->programs_set = 1;
+  return MG_OK;
+}
+
+int mg_get_env_scene(mg_handle* h, int32_t env, mg_scene_t* out) {
+  if (!h || !out) return fail(MG_E_INVALID, "mg_get_env_scene: null argument%s", "");
+  if (env < 0 || env >= h->cfg.batch) return fail(MG_E_INVALID, "mg_get_env_scene: env out of range%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int32_t scene = 0;
+  CUDA_TRY(cudaMemcpyAsync(&scene, &h->d_states[env].scene, sizeof(scene), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(out, &h->d_scenes[scene].s, sizeof(mg_scene_t), cudaMemcpyDeviceToHost));
+  return MG_OK;
+}
+
+int mg_get_poses(mg_handle* h, double* out_host) {
+  if (!h || !out_host) return fail(MG_E_INVALID, "mg_get_poses: null argument%s", "");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpy2DAsync(out_host, sizeof(double4) * MG_MAX_BODIES, &h->d_states[0].P[0], sizeof(EnvState),
+                             sizeof(double4) * MG_MAX_BODIES, (size_t)h->cfg.batch, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return MG_OK;
+}
+
+int mg_sampler_failures(mg_handle* h, int64_t* out) {
+  if (!h || !out) return fail(MG_E_INVALID, "mg_sampler_failures: null argument%s", "");
+  *out = 0;
+  if (!h->cfg.device_sampling) return MG_OK;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  unsigned long long v = 0;
+  CUDA_TRY(cudaMemcpyAsync(&v, h->d_failures, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out = (int64_t)v;
   return MG_OK;
 }
 

@@ -16,6 +16,7 @@
 #include "mg_device.cuh"
 #include "mg_narrowphase.h"
 #include "mg_sincos.h"
+#include "mg_reset.cuh"
 
 __device__ static ShapeView state_view(const EnvState& st, const DeviceScene* ds, int si) {
   const mg_shape_t& sh = ds->s.shapes[si];
@@ -207,29 +208,6 @@ __device__ static double compute_score(const EnvState& st, const DeviceScene* ds
   return 0.0;
 }
 
-__device__ static void reset_state(EnvState& st, const DeviceScene* ds, int scene) {
-  const mg_scene_t& sc = ds->s;
-  st.scene = scene;
-  st.episode_steps = 0;
-  st.stamp = 0;
-  st.n_cache = 0;
-  st.overflow = 0;
-  st.fresh = 1;
-  st.last_contacts = 0;
-  for (int b = 0; b < MG_MAX_BODIES; b++) {
-    double x = 0.0, y = 0.0, a = 0.0, cs = 1.0, sn = 0.0;
-    if (b < sc.n_bodies) {
-      x = sc.bodies[b].p0[0]; y = sc.bodies[b].p0[1]; a = sc.bodies[b].a0;
-      mg_det_sincos(a, &sn, &cs);
-    }
-    st.P[b] = make_double4(x, y, a, 0.0);
-    st.R[b] = make_double2(cs, sn);
-    st.V[b] = make_double4(0.0, 0.0, 0.0, 0.0);
-    st.Bv[b] = make_double4(0.0, 0.0, 0.0, 0.0);
-  }
-  for (int j = 0; j < MG_MAX_JOINTS; j++) st.jacc[j] = make_double2(0.0, 0.0);
-}
-
 /* mode 0: full step tail; mode 1: score of the current state only (mg_score) */
 __device__ __forceinline__ uint32_t mix32(uint32_t x) { /* lowbias32 integer hash */
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
@@ -237,7 +215,7 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) { /* lowbias32 integer has
 }
 
 __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, int env0, int count,
-                         int auto_reset, int mode, int draw_first, int draw_count, uint32_t reset_seed,
+                         int auto_reset, int mode, int draw_first, int draw_count, uint32_t reset_seed, int sample_mode,
                          float* __restrict__ reward,
                          uint8_t* __restrict__ done, float* __restrict__ score,
                          unsigned long long* __restrict__ overflow_count) {
@@ -284,39 +262,45 @@ __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __res
       scene = draw_first +
               (int)(mix32(mix32(reset_seed ^ mix32((uint32_t)env)) + (uint32_t)resets) % (uint32_t)draw_count);
     }
-    reset_state(st, scenes + scene, scene);
+    mg_reset_state(st, scenes + scene, scene);
+    /* device-side layout sampling: `scene` is a template; k_sample_layouts (next on the stream) draws sizes
+     * and poses into the environment's own slot and resets it again from there */
+    if (sample_mode) st.fresh = MG_FRESH_SAMPLE;
   }
 }
 
 /* explicit reset of selected envs (env_ids == nullptr: all), optional new scene index per env */
 __global__ void k_reset(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, int n,
-                        const int32_t* __restrict__ env_ids, const int32_t* __restrict__ scene_ids, int first_time) {
+                        const int32_t* __restrict__ env_ids, const int32_t* __restrict__ scene_ids, int first_time,
+                        int sample_mode) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int env = env_ids ? env_ids[i] : i;
   EnvState& st = states[env];
   int scene = scene_ids ? scene_ids[i] : (first_time ? 0 : st.scene);
-  reset_state(st, scenes + scene, scene);
+  mg_reset_state(st, scenes + scene, scene);
   for (int k = 0; k < MG_NCACHE; k++) {
     CEntry e;
     e.a = e.b = e.used = e.pad_ = 0; e.hash = 0; e.stamp = -100; e.pad2_ = 0; e.jn = e.jt = 0.0;
     st.cache[k] = e;
   }
+  if (sample_mode && !first_time) { st.resets++; st.fresh = MG_FRESH_SAMPLE; }
 }
 
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
-                             int draw_first, int draw_count, uint32_t reset_seed, float* reward, uint8_t* done,
-                             float* score, unsigned long long* overflow_count, cudaStream_t stream) {
+                             int draw_first, int draw_count, uint32_t reset_seed, int sample_mode, float* reward,
+                             uint8_t* done, float* score, unsigned long long* overflow_count, cudaStream_t stream) {
   int threads = 128;
   k_finish<<<(count + threads - 1) / threads, threads, 0, stream>>>(states, scenes, env0, count, auto_reset, mode,
-                                                                    draw_first, draw_count, reset_seed, reward, done,
-                                                                    score, overflow_count);
+                                                                    draw_first, draw_count, reset_seed, sample_mode,
+                                                                    reward, done, score, overflow_count);
   return cudaGetLastError();
 }
 
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
-                            const int32_t* scene_ids, int first_time, cudaStream_t stream) {
+                            const int32_t* scene_ids, int first_time, int sample_mode, cudaStream_t stream) {
   int threads = 128;
-  k_reset<<<(n + threads - 1) / threads, threads, 0, stream>>>(states, scenes, n, env_ids, scene_ids, first_time);
+  k_reset<<<(n + threads - 1) / threads, threads, 0, stream>>>(states, scenes, n, env_ids, scene_ids, first_time,
+                                                               sample_mode);
   return cudaGetLastError();
 }

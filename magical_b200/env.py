@@ -31,9 +31,13 @@ def make_task(env_id):
 
 
 def make_vec(env_id, batch, device=0, auto_reset=True, n_scenes=None,
-             seed=None, stream=None, alloc_obs=True, keep_scene=False):
+             seed=None, stream=None, alloc_obs=True, keep_scene=False,
+             device_sampling=False):
     """Batched GPU env for a registered id.  Demo variants share one scene;
     randomised Test variants pre-sample `n_scenes` scenes (default 64).
+    device_sampling=True (randomised variants): the n_scenes scenes are
+    structure templates and every reset draws fresh goal sizes and poses on
+    the GPU.
     alloc_obs=False leaves the observation buffer to the caller (`bind_obs`,
     e.g. a slice of a multi-GPU global batch); keep_scene=True restarts every
     env on the scene it is bound to instead of redrawing from the pool."""
@@ -43,7 +47,8 @@ def make_vec(env_id, batch, device=0, auto_reset=True, n_scenes=None,
     return MagicalVecEnv(task, batch, preproc=spec.preproc, device=device,
                          auto_reset=auto_reset, n_scenes=n_scenes, seed=seed,
                          stream=stream, alloc_obs=alloc_obs,
-                         keep_scene=keep_scene)
+                         keep_scene=keep_scene,
+                         device_sampling=device_sampling)
 
 
 def make_vec_mixed(env_ids, batch, device=0, auto_reset=True, stream=None,

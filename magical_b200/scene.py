@@ -82,7 +82,22 @@ scene_dt = np.dtype([
 config_dt = np.dtype([('device', 'i4'), ('batch', 'i4'), ('n_scenes', 'i4'),
                       ('obs_mode', 'i4'), ('res', 'i4'), ('auto_reset', 'i4'),
                       ('reserved0_', 'i4'), ('reset_seed', 'i4'),
-                      ('keep_scene', 'i4'), ('reserved_', 'i4', 7)], align=True)
+                      ('keep_scene', 'i4'), ('device_sampling', 'i4'),
+                      ('reserved_', 'i4', 6)], align=True)
+
+MAX_PLACE_ENTS, MAX_PLACE_BODIES = 16, 6
+place_ent_dt = np.dtype([
+    ('kind', 'i4'), ('goal', 'i4'), ('n_bodies', 'i4'), ('n_groups', 'i4'),
+    ('bodies', 'i4', MAX_PLACE_BODIES), ('groups', 'i4', 4),
+    ('rand_pos', 'i4'), ('rand_rot', 'i4'),
+    ('pos_limit', 'f8'), ('rot_limit', 'f8'), ('orig', 'f8', 3)], align=True)
+place_hw_dt = np.dtype([
+    ('goal', 'i4'), ('pad_', 'i4'), ('min_side', 'f8'), ('max_side', 'f8'),
+    ('cur_h', 'f8'), ('cur_w', 'f8'), ('linf', 'f8')], align=True)
+placement_dt = np.dtype([
+    ('n_ents', 'i4'), ('n_hw', 'i4'), ('goal_prims', 'i4', (MAX_GOALS, 2)),
+    ('arena', 'f8', 4), ('ents', place_ent_dt, MAX_PLACE_ENTS),
+    ('hw', place_hw_dt, MAX_GOALS)], align=True)
 
 state_dt = np.dtype([
     ('n_bodies', 'i4'), ('n_joints', 'i4'), ('n_contacts', 'i4'),

@@ -42,7 +42,8 @@ class MagicalVecEnv:
 
     def __init__(self, task, batch, preproc=None, device=0, auto_reset=True,
                  n_scenes=1, seed=None, scenes=None, stream=None,
-                 alloc_obs=True, keep_scene=False, default_scene_ids=None):
+                 alloc_obs=True, keep_scene=False, default_scene_ids=None,
+                 device_sampling=False):
         import torch
         if not torch.cuda.is_available():
             raise _native.NativeError(
@@ -60,6 +61,17 @@ class MagicalVecEnv:
         self.rng = np.random.RandomState(seed)
         if seed is not None:
             task.seed(seed)
+        # device_sampling: the scenes are TEMPLATES (structure + dynamics); every
+        # reset re-samples goal sizes and poses on the device (csrc/mg_sample.cu)
+        self.device_sampling = bool(device_sampling)
+        self.programs = None
+        if self.device_sampling:
+            assert scenes is None and not keep_scene
+            built = [task.build_template() for _ in range(n_scenes)]
+            scenes = [b[0] for b in built]
+            self.programs = np.ascontiguousarray(
+                np.stack([b[1] for b in built])).astype(sc.placement_dt,
+                                                        copy=False)
         if scenes is None:
             scenes = [task.build_scene() for _ in range(n_scenes)]
         self.scenes = np.ascontiguousarray(np.stack(scenes)).astype(
@@ -81,7 +93,8 @@ class MagicalVecEnv:
                                   n_scenes=self.n_scenes, obs_mode=self.mode,
                                   res=res, auto_reset=int(self.auto_reset),
                                   reset_seed=int(self.rng.randint(1 << 31)),
-                                  keep_scene=int(bool(keep_scene)))
+                                  keep_scene=int(bool(keep_scene)),
+                                  device_sampling=int(self.device_sampling))
         import ctypes
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
@@ -107,6 +120,9 @@ class MagicalVecEnv:
         if self.obs is not None:
             _native.check(self._lib.mg_bind_obs(self._h, self.obs.data_ptr(),
                                                 self.obs.numel()))
+        if self.device_sampling:
+            _native.check(self._lib.mg_set_placement(
+                self._h, 0, self.n_scenes, self.programs.ctypes.data))
 
     # -- gym-like batched API ---------------------------------------------
     def reset(self, env_ids=None, scene_ids=None):
@@ -121,6 +137,9 @@ class MagicalVecEnv:
         if scene_ids is None and self.default_scene_ids is not None:
             scene_ids = self.default_scene_ids if env_ids is None \
                 else self.default_scene_ids[env_ids]
+        if scene_ids is None and self.device_sampling:
+            first, count = self._draw    # template ids, always explicit
+            scene_ids = first + self.rng.randint(0, max(count, 1), size=n)
         if scene_ids is None and self.n_scenes > 1 and self._draw[1] > 0:
             # host-side draws respect the draw range, like the device-side
             # redraw of an auto-reset does
@@ -321,6 +340,29 @@ class MagicalVecEnv:
         _native.check(self._lib.mg_get_state(self._h, int(env),
                                              st.ctypes.data))
         return st
+
+    def get_poses(self):
+        """(x, y, angle) of every body of every environment, host float64
+        [batch, MAX_BODIES, 3], in one copy."""
+        out = np.zeros((self.batch, sc.MAX_BODIES, 4), dtype=np.float64)
+        _native.check(self._lib.mg_get_poses(self._h, out.ctypes.data))
+        return out[:, :, :3]
+
+    def get_env_scene(self, env):
+        """The compiled scene record environment `env` is playing right now
+        (with device_sampling: its own sampled layout)."""
+        rec = np.zeros((), dtype=sc.scene_dt)
+        _native.check(self._lib.mg_get_env_scene(self._h, int(env),
+                                                 rec.ctypes.data))
+        return rec
+
+    def sampler_failures(self):
+        """Resets for which the device sampler found no placement within the
+        reference's try / retry limits and played the template's own layout."""
+        import ctypes
+        out = ctypes.c_int64(0)
+        _native.check(self._lib.mg_sampler_failures(self._h, ctypes.byref(out)))
+        return int(out.value)
 
     def set_state(self, env, state):
         """Restore one environment from a `get_state` snapshot (poses,
