@@ -31,7 +31,7 @@ cudaError_t mg_launch_physics_tpe(EnvState* states, const DeviceScene* scenes, c
 size_t mg_tpe_smem_bytes(const TpeLayout* L);
 size_t mg_tpe_spill_doubles_per_env(const TpeLayout* L);
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
-                             int draw_first, int draw_count, uint32_t reset_seed, int sample_mode, float* reward,
+                             int draw_first, int draw_count, uint32_t reset_seed, int slot_base, float* reward,
                              uint8_t* done, float* score, unsigned long long* overflow_count, cudaStream_t stream);
 cudaError_t mg_launch_reset(EnvState* states, const DeviceScene* scenes, int n, const int32_t* env_ids,
                             const int32_t* scene_ids, int first_time, int sample_mode, cudaStream_t stream);
@@ -40,7 +40,7 @@ cudaError_t mg_launch_sample_layouts(EnvState* states, DeviceScene* scenes, cons
                                      cudaStream_t stream);
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, uint8_t* newest,
                              size_t plane_stride, int batch, int res_out, int ecap, int scap, int rcap, int only_fresh,
-                             int push, int env0, int count, cudaStream_t stream);
+                             int push, int env0, int count, int slot_base, cudaStream_t stream);
 cudaError_t mg_launch_stack_push(uint8_t* stacks, const uint8_t* newest, const uint8_t* fresh, long long env_first,
                                  long long env_count, int shard, long long rank_stride, int res, cudaStream_t stream);
 cudaError_t mg_raster_upload_units(const double* units);
@@ -72,6 +72,11 @@ struct mg_handle {
   mg_placement_t* d_programs;
   unsigned long long* d_failures;
   int programs_set;
+  /* the auto-reset sampler runs on its own stream, next to the render of the environments that did not reset
+   * (one warp per resetting environment is latency-bound: ~1.5 ms for a handful of warps) */
+  cudaStream_t sample_stream;
+  cudaEvent_t ev_finish, ev_sampled;
+  int sample_pending;
   /* mg_step software pipeline: the batch is cut into chunks whose physics and raster kernels run on two
    * internal streams, staggered so that the raster of chunk c overlaps the physics of chunk c + 1 (the
    * physics is latency-bound at ~13 % issue utilisation, the raster issue-bound: they share SMs well) */
@@ -307,8 +312,20 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
       return fail(MG_E_CUDA, "mg_create: stream / event creation failed%s", "");
     }
   }
+  if (cfg->device_sampling &&
+      /* highest priority: its few blocks must get the first SM slot the render of the others frees, not the
+       * last one (block scheduling is otherwise first launched, first placed) */
+      (cudaStreamCreateWithPriority(&h->sample_stream, cudaStreamNonBlocking, -5) != cudaSuccess ||
+       cudaEventCreateWithFlags(&h->ev_finish, cudaEventDisableTiming) != cudaSuccess ||
+       cudaEventCreateWithFlags(&h->ev_sampled, cudaEventDisableTiming) != cudaSuccess)) {
+    mg_destroy(h);
+    return fail(MG_E_CUDA, "mg_create: stream / event creation failed%s", "");
+  }
   if ((e = cudaMemcpyAsync(h->d_scenes, host.data(), sizeof(DeviceScene) * (size_t)cfg->n_scenes, cudaMemcpyHostToDevice,
                            h->stream)) != cudaSuccess ||
+      (cfg->device_sampling && /* slots are empty scenes until the first reset samples them */
+       (e = cudaMemsetAsync(h->d_scenes + cfg->n_scenes, 0, sizeof(DeviceScene) * (size_t)cfg->batch, h->stream)) !=
+           cudaSuccess) ||
       (e = cudaMemsetAsync(h->d_states, 0, sizeof(EnvState) * (size_t)cfg->batch, h->stream)) != cudaSuccess) {
     mg_destroy(h);
     return fail(MG_E_CUDA, "mg_create: upload: %s", cudaGetErrorString(e));
@@ -346,6 +363,9 @@ int mg_destroy(mg_handle* h) {
   cudaFree(h->d_overflow);
   cudaFree(h->d_programs);
   cudaFree(h->d_failures);
+  if (h->sample_stream) { cudaStreamSynchronize(h->sample_stream); cudaStreamDestroy(h->sample_stream); }
+  if (h->ev_finish) cudaEventDestroy(h->ev_finish);
+  if (h->ev_sampled) cudaEventDestroy(h->ev_sampled);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   for (int i = 0; i < 2; i++) {
     if (h->side[i]) { cudaStreamSynchronize(h->side[i]); cudaStreamDestroy(h->side[i]); }
@@ -412,11 +432,32 @@ int mg_stack_push(void* stacks_dev, const void* newest_dev, const uint8_t* fresh
 
 int64_t mg_obs_nbytes(const mg_handle* h) { return h ? h->obs_bytes : -1; }
 
+/* the caller's stream waits for an auto-reset sampler that is still running on the side stream */
+static int join_sampler(mg_handle* h) {
+  if (h->sample_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_sampled, 0));
+    h->sample_pending = 0;
+  }
+  return MG_OK;
+}
+
 static int do_raster(mg_handle* h, int only_fresh, int push) {
   if (!h->obs) return fail(MG_E_STATE, "no observation buffer bound (call mg_bind_obs first)%s", "");
+  const int slot_base = h->cfg.device_sampling ? h->cfg.n_scenes : -1;
+  if (h->sample_pending && only_fresh == 0) {
+    /* render everything that did NOT reset while the sampler is still placing the environments that did
+     * (only_fresh = 2 skips them), then their first frames */
+    CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->newest, (size_t)h->plane_stride,
+                              h->cfg.batch, h->res_out, h->ecap, h->scap, h->rcap, 2, push, 0, h->cfg.batch, slot_base,
+                              h->stream));
+    h->launches++;
+    only_fresh = 1;
+  }
+  int rc = join_sampler(h);
+  if (rc != MG_OK) return rc;
   CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->newest, (size_t)h->plane_stride,
                             h->cfg.batch, h->res_out, h->ecap, h->scap, h->rcap, only_fresh, push, 0, h->cfg.batch,
-                            h->stream));
+                            slot_base, h->stream));
   h->launches++;
   return MG_OK;
 }
@@ -424,6 +465,7 @@ static int do_raster(mg_handle* h, int only_fresh, int push) {
 int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* scene_ids) {
   if (!h) return fail(MG_E_INVALID, "mg_reset: null handle%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  { int rc_ = join_sampler(h); if (rc_ != MG_OK) return rc_; }
   if (!env_ids) n = h->cfg.batch;
   if (n < 0 || n > h->cfg.batch) return fail(MG_E_INVALID, "mg_reset: bad env count%s", "");
   if (n == 0) return MG_OK;
@@ -457,6 +499,7 @@ int mg_reset(mg_handle* h, const int32_t* env_ids, int32_t n, const int32_t* sce
 static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_dev, uint8_t* done_dev, float* score_dev) {
   if (!actions_dev) return fail(MG_E_INVALID, "mg_step: null actions%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  { int rc = join_sampler(h); if (rc != MG_OK) return rc; }
   if (h->use_tpe)
     CUDA_TRY(mg_launch_physics_tpe(h->d_states, h->d_scenes, actions_dev, 0, h->cfg.batch, &h->tpe, h->d_spill,
                                    h->d_scratch, h->stream));
@@ -464,13 +507,18 @@ static int do_physics(mg_handle* h, const int32_t* actions_dev, float* reward_de
     CUDA_TRY(mg_launch_physics(h->d_states, h->d_scenes, actions_dev, h->cfg.batch, h->lanes_per_env, h->block_threads,
                                h->stream));
   CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, h->cfg.auto_reset, 0, h->draw_first, h->draw_count,
-                            (uint32_t)h->cfg.reset_seed, h->cfg.device_sampling, reward_dev, done_dev, score_dev,
-                            h->d_overflow, h->stream));
+                            (uint32_t)h->cfg.reset_seed, h->cfg.device_sampling ? h->cfg.n_scenes : -1, reward_dev, done_dev,
+                            score_dev, h->d_overflow, h->stream));
   h->launches += 2;
   if (h->cfg.device_sampling && h->cfg.auto_reset) {
-    /* environments that finished an episode get a freshly sampled layout before the render */
+    /* environments that finished an episode get a freshly sampled layout, on the side stream: the render of
+     * all the others (do_raster) runs next to it */
+    CUDA_TRY(cudaEventRecord(h->ev_finish, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->sample_stream, h->ev_finish, 0));
     CUDA_TRY(mg_launch_sample_layouts(h->d_states, h->d_scenes, h->d_programs, h->cfg.n_scenes, h->cfg.batch,
-                                      (uint32_t)h->cfg.reset_seed, h->d_failures, h->stream));
+                                      (uint32_t)h->cfg.reset_seed, h->d_failures, h->sample_stream));
+    CUDA_TRY(cudaEventRecord(h->ev_sampled, h->sample_stream));
+    h->sample_pending = 1;
     h->launches++;
   }
   return MG_OK;
@@ -498,9 +546,9 @@ static int step_pipelined(mg_handle* h, const int32_t* actions_dev, float* rewar
                                    st));
     CUDA_TRY(cudaEventRecord(h->ev_phys[c & 1], st));
     CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, env0, count, h->cfg.auto_reset, 0, h->draw_first, h->draw_count,
-                              (uint32_t)h->cfg.reset_seed, 0, reward_dev, done_dev, score_dev, h->d_overflow, st));
+                              (uint32_t)h->cfg.reset_seed, -1, reward_dev, done_dev, score_dev, h->d_overflow, st));
     CUDA_TRY(mg_launch_raster(h->cfg.obs_mode, h->d_states, h->d_scenes, h->obs, h->newest, (size_t)h->plane_stride, B,
-                              h->res_out, h->ecap, h->scap, h->rcap, 0, 1, env0, count, st));
+                              h->res_out, h->ecap, h->scap, h->rcap, 0, 1, env0, count, -1, st));
     h->launches += 3;
   }
   for (int i = 0; i < 2; i++) {
@@ -539,8 +587,9 @@ int mg_render(mg_handle* h) {
 int mg_score(mg_handle* h, float* score_dev) {
   if (!h || !score_dev) return fail(MG_E_INVALID, "mg_score: null argument%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, 0, 1, 0, 1, 0u, 0, nullptr, nullptr, score_dev, nullptr,
-                            h->stream));
+  { int rc_ = join_sampler(h); if (rc_ != MG_OK) return rc_; }
+  CUDA_TRY(mg_launch_finish(h->d_states, h->d_scenes, 0, h->cfg.batch, 0, 1, 0, 1, 0u,
+                            h->cfg.device_sampling ? h->cfg.n_scenes : -1, nullptr, nullptr, score_dev, nullptr, h->stream));
   h->launches++;
   return MG_OK;
 }
@@ -549,6 +598,7 @@ int mg_get_state(mg_handle* h, int32_t env, mg_state_t* out) {
   if (!h || !out) return fail(MG_E_INVALID, "mg_get_state: null argument%s", "");
   if (env < 0 || env >= h->cfg.batch) return fail(MG_E_INVALID, "mg_get_state: env out of range%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  { int rc_ = join_sampler(h); if (rc_ != MG_OK) return rc_; }
   EnvState st;
   CUDA_TRY(cudaMemcpyAsync(&st, h->d_states + env, sizeof(EnvState), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -677,9 +727,11 @@ int mg_get_env_scene(mg_handle* h, int32_t env, mg_scene_t* out) {
   if (!h || !out) return fail(MG_E_INVALID, "mg_get_env_scene: null argument%s", "");
   if (env < 0 || env >= h->cfg.batch) return fail(MG_E_INVALID, "mg_get_env_scene: env out of range%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  { int rc_ = join_sampler(h); if (rc_ != MG_OK) return rc_; }
   int32_t scene = 0;
   CUDA_TRY(cudaMemcpyAsync(&scene, &h->d_states[env].scene, sizeof(scene), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->cfg.device_sampling) scene = h->cfg.n_scenes + env; /* the environment's own sampled layout */
   CUDA_TRY(cudaMemcpy(out, &h->d_scenes[scene].s, sizeof(mg_scene_t), cudaMemcpyDeviceToHost));
   return MG_OK;
 }
@@ -687,6 +739,7 @@ int mg_get_env_scene(mg_handle* h, int32_t env, mg_scene_t* out) {
 int mg_get_poses(mg_handle* h, double* out_host) {
   if (!h || !out_host) return fail(MG_E_INVALID, "mg_get_poses: null argument%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  { int rc_ = join_sampler(h); if (rc_ != MG_OK) return rc_; }
   CUDA_TRY(cudaMemcpy2DAsync(out_host, sizeof(double4) * MG_MAX_BODIES, &h->d_states[0].P[0], sizeof(EnvState),
                              sizeof(double4) * MG_MAX_BODIES, (size_t)h->cfg.batch, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -718,6 +771,7 @@ int64_t mg_launch_count(const mg_handle* h) { return h ? h->launches : 0; }
 int mg_overflow_count(mg_handle* h, int64_t* out) {
   if (!h || !out) return fail(MG_E_INVALID, "mg_overflow_count: null argument%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  { int rc_ = join_sampler(h); if (rc_ != MG_OK) return rc_; }
   unsigned long long v = 0;
   CUDA_TRY(cudaMemcpyAsync(&v, h->d_overflow, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -728,6 +782,7 @@ int mg_overflow_count(mg_handle* h, int64_t* out) {
 int mg_synchronize(mg_handle* h) {
   if (!h) return fail(MG_E_INVALID, "mg_synchronize: null handle%s", "");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
+  { int rc_ = join_sampler(h); if (rc_ != MG_OK) return rc_; }
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return MG_OK;
 }

@@ -215,7 +215,7 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) { /* lowbias32 integer has
 }
 
 __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, int env0, int count,
-                         int auto_reset, int mode, int draw_first, int draw_count, uint32_t reset_seed, int sample_mode,
+                         int auto_reset, int mode, int draw_first, int draw_count, uint32_t reset_seed, int slot_base,
                          float* __restrict__ reward,
                          uint8_t* __restrict__ done, float* __restrict__ score,
                          unsigned long long* __restrict__ overflow_count) {
@@ -223,7 +223,9 @@ __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __res
   if (env >= count) return;
   env += env0; /* this launch covers environments [env0, env0 + count) */
   EnvState& st = states[env];
-  const DeviceScene* ds = scenes + st.scene;
+  /* device-side layout sampling (slot_base >= 0): the environment's sampled goal sensors live in its slot */
+  const bool sample_mode = slot_base >= 0;
+  const DeviceScene* ds = scenes + (sample_mode ? slot_base + env : st.scene);
   const mg_scene_t& sc = ds->s;
   if (mode == 1) {
     if (score) score[env] = (float)compute_score(st, ds);
@@ -256,6 +258,7 @@ __global__ void k_finish(EnvState* __restrict__ states, const DeviceScene* __res
   if (score) score[env] = (float)s;
   if (d && auto_reset) {
     int scene = st.scene;
+    if (sample_mode && !(draw_count > 0 && (draw_count > 1 || draw_first != scene))) ++st.resets;
     if (draw_count > 0 && (draw_count > 1 || draw_first != scene)) {
       /* randomised variants: the next episode plays a freshly drawn scene of the pool's current draw range */
       const int resets = ++st.resets;
@@ -288,11 +291,11 @@ __global__ void k_reset(EnvState* __restrict__ states, const DeviceScene* __rest
 }
 
 cudaError_t mg_launch_finish(EnvState* states, const DeviceScene* scenes, int env0, int count, int auto_reset, int mode,
-                             int draw_first, int draw_count, uint32_t reset_seed, int sample_mode, float* reward,
+                             int draw_first, int draw_count, uint32_t reset_seed, int slot_base, float* reward,
                              uint8_t* done, float* score, unsigned long long* overflow_count, cudaStream_t stream) {
   int threads = 128;
   k_finish<<<(count + threads - 1) / threads, threads, 0, stream>>>(states, scenes, env0, count, auto_reset, mode,
-                                                                    draw_first, draw_count, reset_seed, sample_mode,
+                                                                    draw_first, draw_count, reset_seed, slot_base,
                                                                     reward, done, score, overflow_count);
   return cudaGetLastError();
 }

@@ -686,7 +686,7 @@ template <int MODE>
 __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_BLOCKS)
 k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, uint8_t* __restrict__ obs,
          uint8_t* __restrict__ newest, size_t plane_stride /* bytes between the two view planes of obs */, int batch,
-         int res_out, int ecap, int scap, int rcap, int only_fresh, int push, int env0) {
+         int res_out, int ecap, int scap, int rcap, int only_fresh, int push, int env0, int slot_base) {
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
   /* LoResStack and RAW keep their two views in separate planes, so the views are rendered one after the
    * other through the same shared memory (NPASS = 2, one resident view): half the footprint, twice the CTAs
@@ -701,8 +701,13 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   if (env >= batch) return;
   EnvState& stg = states[env];
   const EnvState& st = stg;
-  if (only_fresh && st.fresh == 0) return; /* block-uniform: after mg_reset only the reset envs are redrawn */
-  const mg_scene_t& sc = scenes[st.scene].s;
+  /* block-uniform.  only_fresh 1: after a reset only the reset envs are (re)drawn; 2: everything EXCEPT the envs
+   * that just reset (their layout is still being sampled on another stream; they are drawn by a second launch) */
+  if (only_fresh == 1 && st.fresh == 0) return;
+  if (only_fresh == 2 && st.fresh != 0) return;
+  /* device-side layout sampling (slot_base >= 0): the sampled goal rectangles live in the environment's slot */
+  const int scene_index = slot_base >= 0 ? slot_base + env : st.scene;
+  const mg_scene_t& sc = scenes[scene_index].s;
   const float px_scale = (float)(res_out * SS) / 384.0f;
 
   /* carve shared memory per view */
@@ -725,7 +730,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   for (int pass = 0; pass < NPASS; pass++) {
   for (int v = 0; v < NV; v++) {
     int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
-    build_view<SS>(vsm[v], st, sc, scenes[st.scene].ra, view, res_out, ecap, scap, s_off, s_misc);
+    build_view<SS>(vsm[v], st, sc, scenes[scene_index].ra, view, res_out, ecap, scap, s_off, s_misc);
     if (threadIdx.x == 0) { s_misc[4] = 0; s_misc[5] = 0; s_misc[6] = 0; } /* flat / heavy / light list lengths */
     __syncthreads();
   }
@@ -991,24 +996,24 @@ cudaError_t mg_raster_upload_units(const double* units /* [130][2] */) {
 template <int MODE>
 static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint8_t* obs, uint8_t* newest,
                                size_t plane_stride, int batch, int res_out, int ecap, int scap, int rcap,
-                               int only_fresh, int push, int env0, int count, cudaStream_t stream) {
+                               int only_fresh, int push, int env0, int count, int slot_base, cudaStream_t stream) {
   size_t smem = mg_raster_smem_bytes(MODE, ecap, scap, rcap);
   cudaError_t e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   k_raster<MODE><<<count, RASTER_THREADS, smem, stream>>>(states, scenes, obs, newest, plane_stride, batch, res_out, ecap,
-                                                          scap, rcap, only_fresh, push, env0);
+                                                          scap, rcap, only_fresh, push, env0, slot_base);
   return cudaGetLastError();
 }
 
 cudaError_t mg_launch_raster(int mode, EnvState* states, const DeviceScene* scenes, uint8_t* obs, uint8_t* newest,
                              size_t plane_stride, int batch, int res_out, int ecap, int scap, int rcap, int only_fresh,
-                             int push, int env0, int count, cudaStream_t stream) {
+                             int push, int env0, int count, int slot_base, cudaStream_t stream) {
 #define MG_RASTER_CASE(M)                                                                                            \
   case M:                                                                                                            \
     return launch_mode<M>(states, scenes, obs, newest, plane_stride, batch, res_out, ecap, scap, rcap, only_fresh, push, \
-                          env0, count, stream);
+                          env0, count, slot_base, stream);
   switch (mode) {
     MG_RASTER_CASE(MG_OBS_LORES4E)
     MG_RASTER_CASE(MG_OBS_LORES4A)
