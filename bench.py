@@ -373,8 +373,11 @@ class Runner:
             if env._newest_ready:
                 # p2p transport: k_stack_push_p2p reads the frames over NVLink itself and `exchange` is the flag
                 # barrier + the 12 B/env scalars; nccl transport: `exchange` is the two ncclAllGathers
-                km['k_stack_push'] = self.time_loop(lambda i: env.push_only(), n_k)
+                # the push is timed behind the flag barrier, as in a step: ranks that start together walk
+                # their peers in the staggered ring order (no NVLink egress hot spot)
                 km['exchange'] = self.time_loop(lambda i: env.gather_only(), n_k)
+                km['k_stack_push'] = self.time_loop(lambda i: (env.gather_only(), env.push_only()), n_k) \
+                    - km['exchange']
             res['kernel_ms'] = km
         res['overflow_envs'] = int(venv.overflow_count())
         return res
@@ -487,9 +490,13 @@ def run_b200(args):
     torch.cuda.empty_cache()
 
     # ---- further records of the same run (N>1): BASELINE configs[4] and the weak-scaling headline workload
-    if world > 1 and not args.no_records and args.workload is None:
+    if not args.no_records and args.workload is None:
         records = []
-        for rname, rgather in (('config5', 'newest'), ('cluster65536', 'newest'), ('cluster65536', False)):
+        # N>1: BASELINE configs[4] and the weak-scaling headline workload with / without the observation gather;
+        # N=1: configs[3] and [4] on one GPU, the base points of their strong-scaling curves
+        plan = (('config5', 'newest'), ('cluster65536', 'newest'), ('cluster65536', False)) if world > 1 \
+            else (('config4', False), ('config5', False))
+        for rname, rgather in plan:
             r = Runner(args, rname, rgather)
             rr = r.measure(K, W, e2e=True, kernels=True)
             records.append({

@@ -410,9 +410,13 @@ void* mg_comm_frame_ptr(mg_comm* c, int32_t buffer);
 int mg_comm_barrier(mg_comm* c, void* cuda_stream);
 int mg_comm_gather_scalars(mg_comm* c, int32_t buffer, void* dst_dev, void* cuda_stream);
 /* stacks_dev: u8 [n_global, res, res, 12] (one view plane); the frame of env e is read from rank e / shard at
- * byte view_offset + (e % shard) * res * res * 3 of its frame buffer `buffer`. */
+ * byte view_offset + (e % shard) * res * res * 3 of its frame buffer `buffer`.  env_modulo = world * shard makes
+ * the range [env_first, env_first + env_count) wrap around: rank r passes env_first = (r + 1) * shard and
+ * env_count = (world - 1) * shard and so reads its peers in the order r+1, r+2, ... -- every rank starts at a
+ * different owner, no GPU's NVLink egress serves all readers at once.  env_modulo = 0: no wrap. */
 int mg_comm_stack_push(mg_comm* c, int32_t buffer, int64_t view_offset, void* stacks_dev, const uint8_t* fresh_dev,
-                       int64_t env_first, int64_t env_count, int32_t shard, int32_t res, void* cuda_stream);
+                       int64_t env_first, int64_t env_count, int64_t env_modulo, int32_t shard, int32_t res,
+                       void* cuda_stream);
 int mg_comm_error(mg_comm* c, int32_t* out);
 int mg_comm_destroy(mg_comm* c);
 

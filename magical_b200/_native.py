@@ -84,7 +84,7 @@ def load():
     L.mg_comm_frame_ptr.argtypes = [vp, i32]
     L.mg_comm_barrier.argtypes = [vp, vp]
     L.mg_comm_gather_scalars.argtypes = [vp, i32, vp, vp]
-    L.mg_comm_stack_push.argtypes = [vp, i32, i64, vp, vp, i64, i64, i32, i32, vp]
+    L.mg_comm_stack_push.argtypes = [vp, i32, i64, vp, vp, i64, i64, i64, i32, i32, vp]
     L.mg_comm_error.argtypes = [vp, vp]
     L.mg_comm_destroy.argtypes = [vp]
     L.mg_score.argtypes = [vp, vp]

@@ -104,10 +104,13 @@ k_peer_gather(const __grid_constant__ PeerPtrs peers, int64_t offset, uint4* __r
 __global__ void __launch_bounds__(256)
 k_stack_push_p2p(uint8_t* __restrict__ stacks, const __grid_constant__ PeerPtrs peers, int64_t frames_offset /* of this buffer + view */,
                  const uint8_t* __restrict__ fresh, long long env_first, long long n_groups_total, int groups_per_env,
-                 int shard) {
+                 int shard, long long env_modulo) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups_total) return;
-  const long long env = env_first + g / groups_per_env;
+  /* env_modulo > 0: the range wraps around, so that rank r can walk its peers in the order r+1, r+2, ...:
+   * with every rank starting at a different owner no GPU's NVLink egress serves all readers at once */
+  long long env = env_first + g / groups_per_env;
+  if (env_modulo > 0 && env >= env_modulo) env -= env_modulo;
   const int gi = (int)(g % groups_per_env);
   const uint32_t* np_ = reinterpret_cast<const uint32_t*>(peers.p[env / shard] + frames_offset +
                                                           ((env % shard) * (long long)groups_per_env + gi) * 12);
@@ -226,13 +229,16 @@ int mg_comm_gather_scalars(mg_comm* c, int32_t buffer, void* dst_dev, void* cuda
 }
 
 int mg_comm_stack_push(mg_comm* c, int32_t buffer, int64_t view_offset, void* stacks_dev, const uint8_t* fresh_dev,
-                       int64_t env_first, int64_t env_count, int32_t shard, int32_t res, void* cuda_stream) {
+                       int64_t env_first, int64_t env_count, int64_t env_modulo, int32_t shard, int32_t res,
+                       void* cuda_stream) {
   if (!c || !c->connected || !stacks_dev || buffer < 0 || buffer >= c->n_buf)
     return cfail(MG_E_INVALID, "mg_comm_stack_push: bad argument", nullptr);
   if (env_count <= 0) return MG_OK;
   const int gpe = res * res / 4;
   if (res <= 0 || gpe % 32 != 0 || shard <= 0 || env_first < 0 || (view_offset & 15) != 0 ||
-      (env_first + env_count + shard - 1) / shard > c->world || ((uintptr_t)stacks_dev & 15) != 0)
+      (env_modulo == 0 && (env_first + env_count + shard - 1) / shard > c->world) ||
+      (env_modulo != 0 && (env_modulo != (int64_t)shard * c->world || env_first >= env_modulo || env_count > env_modulo)) ||
+      ((uintptr_t)stacks_dev & 15) != 0)
     return cfail(MG_E_INVALID, "mg_comm_stack_push: bad range / alignment", nullptr);
   const long long total = env_count * gpe;
   const long long blocks = (total + 255) / 256;
@@ -240,7 +246,7 @@ int mg_comm_stack_push(mg_comm* c, int32_t buffer, int64_t view_offset, void* st
   k_stack_push_p2p<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(
       (uint8_t*)stacks_dev, c->peers,
       MG_COMM_FLAG_BYTES + c->buf_stride * buffer + align256(c->scalar_bytes) + view_offset, fresh_dev, env_first, total,
-      gpe, shard);
+      gpe, shard, env_modulo);
   COMM_TRY(cudaGetLastError());
   return MG_OK;
 }

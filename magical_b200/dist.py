@@ -154,11 +154,11 @@ class PeerTransport:
         assert dst.is_contiguous() and dst.numel() == self.world * self.scalar_bytes
         self._check(self._lib.mg_comm_gather_scalars(self._h, k, dst.data_ptr(), self._stream()))
 
-    def stack_push(self, k, view, stacks, fresh, first, count):
+    def stack_push(self, k, view, stacks, fresh, first, count, modulo=0):
         self._check(self._lib.mg_comm_stack_push(
             self._h, k, view * self.n * self.frame_bytes, stacks.data_ptr(),
-            None if fresh is None else fresh.data_ptr(), int(first), int(count), self.n, self.hw[0],
-            self._stream()))
+            None if fresh is None else fresh.data_ptr(), int(first), int(count), int(modulo), self.n,
+            self.hw[0], self._stream()))
 
     def error(self):
         import ctypes
@@ -336,14 +336,18 @@ class ShardedVecEnv:
         rank_stride = self.views * n * self._frame_bytes
         for v in range(self.views):
             stacks = self._global[v] if self.views == 2 else self._global
+            if self._peer is not None:
+                # one launch over all remote shards, starting at the NEXT rank and
+                # wrapping around: every rank reads a different owner at any time
+                self._peer.stack_push(k, v, stacks, fresh, self.stop % self.total,
+                                      self.total - n, modulo=self.total)
+                self.push_launches += 1
+                continue
             for first, count in ((0, self.start), (self.stop, self.total - self.stop)):
                 if count <= 0:
                     continue
-                if self._peer is not None:
-                    self._peer.stack_push(k, v, stacks, fresh, first, count)
-                else:
-                    newest = self._recv.view(-1)[v * n * self._frame_bytes:]
-                    self._stack_push(stacks, newest, fresh, first, count, n, rank_stride)
+                newest = self._recv.view(-1)[v * n * self._frame_bytes:]
+                self._stack_push(stacks, newest, fresh, first, count, n, rank_stride)
                 self.push_launches += 1
 
     def _exchange(self, k):
