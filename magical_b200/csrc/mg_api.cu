@@ -179,6 +179,14 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(MG_E_INVALID, "mg_create: no such CUDA device%s", "");
   CUDA_TRY(cudaSetDevice(cfg->device));
+  {
+    /* the library holds sm_100a SASS only (no PTX): say so instead of failing at the first launch */
+    int major = 0, minor = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, cfg->device));
+    if (major != 10 || minor != 0)
+      return fail(MG_E_INVALID, "mg_create: this build contains sm_100a (B200) code only; the selected device is not sm_100%s", "");
+  }
 
   /* derive per-scene constants on the host */
   std::vector<DeviceScene> host(cfg->n_scenes);
