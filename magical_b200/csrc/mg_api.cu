@@ -278,6 +278,8 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
     h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, max_pairs, kcon, nitems, scratch_global);
     while (mg_tpe_smem_bytes(&h->tpe) > 200 * 1024 && kcon > 1)
       h->tpe = tpe_make_layout(max_slots, max_blocks, max_groups, max_pairs, --kcon, nitems, scratch_global);
+    /* residency experiments: unused words at the end of every environment's private area */
+    if (const char* ev = getenv("MG_TPE_PAD_WORDS")) h->tpe.words += atoi(ev);
   }
   cudaError_t e;
   if ((e = cudaMalloc(&h->d_states, sizeof(EnvState) * (size_t)cfg->batch)) != cudaSuccess ||

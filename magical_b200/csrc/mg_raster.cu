@@ -231,7 +231,10 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   const int nrp = min((int)ra.nrp, vs.rcap);
   for (int i = tid; i < RGRID * RGRID * vs.rwords; i += nt) vs.tiles[i] = 0u;
   for (int i = tid; i < RGRID * RGRID; i += nt) vs.cover[i] = -1;
-  if (tid == 0) s_misc[7] = 0; /* number of thick line segments collected by phase C */
+  if (tid == 0) {
+    s_misc[7] = 0; /* number of thick line segments collected by phase C */
+    s_misc[8] = 0; s_misc[9] = 0; s_misc[10] = 0; s_misc[11] = 0; /* flat / heavy / light tile lists, busy-tile hand-out */
+  }
   /* B: window-space vertices */
   for (int v = tid; v < nv; v += nt) {
     const float2 l = *reinterpret_cast<const float2*>(ra.lv[v]);
@@ -696,7 +699,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   constexpr int NPASS = SEQ ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_off[RLONG]; /* long-edge list; last RMAXLINES entries: thick line segments; later the tile lists */
-  __shared__ int s_misc[8];
+  __shared__ int s_misc[12];
   const int env = env0 + blockIdx.x; /* this launch covers environments [env0, env0 + gridDim.x) */
   if (env >= batch) return;
   EnvState& stg = states[env];
@@ -731,8 +734,6 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   for (int v = 0; v < NV; v++) {
     int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
     build_view<SS>(vsm[v], st, sc, scenes[scene_index].ra, view, res_out, ecap, scap, s_off, s_misc);
-    if (threadIdx.x == 0) { s_misc[4] = 0; s_misc[5] = 0; s_misc[6] = 0; } /* flat / heavy / light list lengths */
-    __syncthreads();
   }
   RPROF_DECL
   const int T = res_out / RGRID;        /* output pixels per tile side (multiple of 4) */
@@ -770,14 +771,12 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
     }
     /* busy tiles: the heavy ones (robot, piled-up blocks) fill the list from the front and are handed out
      * first, the light ones from the back: longest-processing-time-first keeps the tail of G2 short */
-    if (all_flat) flat_list[atomicAdd(&s_misc[4], 1)] = (uint8_t)tile;
-    else if (weight >= 5) busy_list[atomicAdd(&s_misc[5], 1)] = (uint8_t)tile;
-    else busy_list[RGRID * RGRID - 1 - atomicAdd(&s_misc[6], 1)] = (uint8_t)tile;
+    if (all_flat) flat_list[atomicAdd(&s_misc[8], 1)] = (uint8_t)tile;
+    else if (weight >= 5) busy_list[atomicAdd(&s_misc[9], 1)] = (uint8_t)tile;
+    else busy_list[RGRID * RGRID - 1 - atomicAdd(&s_misc[10], 1)] = (uint8_t)tile;
   }
   __syncthreads();
-  const int n_flat = s_misc[4], n_heavy = s_misc[5], n_busy = n_heavy + s_misc[6];
-  __syncthreads(); /* s_misc[4] becomes the busy-tile hand-out counter */
-  if (threadIdx.x == 0) s_misc[4] = 0;
+  const int n_flat = s_misc[8], n_heavy = s_misc[9], n_busy = n_heavy + s_misc[10];
   RPROF(8);
   RCOUNT(8, threadIdx.x == 0 ? n_flat : 0); RCOUNT(9, threadIdx.x == 0 ? n_busy : 0);
 
@@ -920,7 +919,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       item = next;
     }
   }
-  __syncthreads(); /* the hand-out counter is reset */
+  /* no barrier: a warp that runs out of flat items starts on the busy tiles (own hand-out counter) */
   RPROF(9);
 
   /* G2: busy tiles, handed out dynamically to half-warps: all 16 lanes walk the same primitive list */
@@ -928,7 +927,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
   for (;;) {
     int bi = 0;
-    if (hl == 0) bi = atomicAdd(&s_misc[4], 1);
+    if (hl == 0) bi = atomicAdd(&s_misc[11], 1);
     bi = __shfl_sync(hmask, bi, 0, 16);
     if (bi >= n_busy) break;
     const int tile = busy_list[bi < n_heavy ? bi : RGRID * RGRID - 1 - (bi - n_heavy)];
@@ -964,7 +963,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       store_group(X0, Y, pre, col);
     }
   }
-  __syncthreads(); /* the next pass rebuilds the shared tables */
+  if (pass + 1 < NPASS) __syncthreads(); /* the next pass rebuilds the shared tables */
   RPROF(7);
   } /* pass */
   if (threadIdx.x == 0 && fresh) stg.fresh = 0;
