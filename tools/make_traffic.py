@@ -2,10 +2,11 @@
 """profiles/traffic.json from an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv`
 log of the bench workload: DRAM bytes (read + write) per launch of each kernel.
 
-The MEDIAN launch is reported, not the mean: the log also holds the reset render (k_raster with
-only_fresh = 1 touches 1/240 of the batch in the prelude) and cold first launches, which must not dilute the
-steady-state figure (the round-1 mean came out at 0.87x algorithmic where the
-steady-state launches are 1.146x)."""
+The median of the FULL launches is reported, not the mean: the log also holds the reset renders (k_raster
+with only_fresh = 1 touches 1/240 of the batch in the prelude) and cold first launches, which must not dilute
+the steady-state figure (the round-1 mean came out at 0.87x algorithmic where the
+steady-state launches are 1.146x).  A launch counts as full when it moves at least half of what the kernel's
+largest launch moves."""
 import collections
 import csv
 import json
@@ -26,10 +27,10 @@ for r in rows[1:]:
 out, detail = {}, {}
 for name, launches in per_launch.items():
     tot = sorted(v['r'] + v['w'] for v in launches.values())
-    med = statistics.median(tot)
+    steady = [v for v in launches.values() if v['r'] + v['w'] >= 0.5 * tot[-1]]
+    med = statistics.median(v['r'] + v['w'] for v in steady)
     out[name] = med
-    steady = [v for v in launches.values() if v['r'] + v['w'] >= 0.5 * med]
-    detail[name] = {'launches': len(tot), 'median_total': med,
+    detail[name] = {'launches': len(tot), 'full_launches': len(steady), 'median_total': med,
                     'median_read': statistics.median(v['r'] for v in steady),
                     'median_write': statistics.median(v['w'] for v in steady),
                     'min_total': tot[0], 'max_total': tot[-1]}
