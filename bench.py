@@ -145,7 +145,12 @@ def _oracle_worker(args):
             if spec.preproc != 'LoRes4A':
                 downsample4(ego)
             if done:
-                orc.reset()
+                if magical.EnvName(env_id).is_test:
+                    # the reference samples a fresh layout at every reset (base_env.py:177-234)
+                    orc.close()
+                    orc = OracleEnv(task.build_scene())
+                else:
+                    orc.reset()
             n += 1
     return n, time.perf_counter() - t0
 
@@ -166,7 +171,7 @@ def cpu_baseline(env_id, seconds, cores):
     return sum(n / dt for n, dt in res)
 
 
-def run_reference(args, env_id, batch):
+def run_reference(args, env_id, batch, kind='per_gpu'):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -195,10 +200,10 @@ def run_reference(args, env_id, batch):
         'ms_per_step': 1000.0 * float(np.median(walls)),
         'seconds_per_batch_step_extrapolated': batch / value,
         'spread': {'min': float(np.min(vals)), 'max': float(np.max(vals)), 'n': len(vals)},
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'higher_is_better': True, 'scaling': 'weak' if kind == 'per_gpu' else 'strong', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'{env_id}, random actions, auto-reset; bounded sample of the batch-{batch} '
-                               'workload, one env per host core'},
+                               f'({"per GPU" if kind == "per_gpu" else "global"}) workload, one env per host core'},
         'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores,
                          'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'env-steps/s',
@@ -543,8 +548,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
         world = int(os.environ.get('WORLD_SIZE', '1'))
-        env_id, batch, _ = WORKLOADS[args.workload or ('cluster65536' if max(world, args.gpus) == 1 else 'config4')]
-        run_reference(args, env_id, args.batch or batch)
+        env_id, batch, kind = WORKLOADS[args.workload or ('cluster65536' if max(world, args.gpus) == 1 else 'config4')]
+        run_reference(args, env_id, args.batch or batch, kind)
     else:
         run_b200(args)
 
