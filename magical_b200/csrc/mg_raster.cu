@@ -221,7 +221,8 @@ template <int SS>
 __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& sc, const mg_raster_aux_t& ra, int view,
                            int res_out, int ecap, int scap, int* s_off /* [RLONG] */, int* s_misc) {
   RPROF_DECL
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x;
+  constexpr int nt = RASTER_THREADS; /* compile-time block size: no runtime divisions by the warp count */
   const int np = sc.n_prims;
   const int res_full = res_out * SS;
   const Camera cam = make_camera(st, sc, view, res_full);
@@ -689,7 +690,10 @@ template <int MODE>
 __global__ void __launch_bounds__(RASTER_THREADS, RASTER_MIN_BLOCKS)
 k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, uint8_t* __restrict__ obs,
          uint8_t* __restrict__ newest, size_t plane_stride /* bytes between the two view planes of obs */, int batch,
-         int res_out, int ecap, int scap, int rcap, int only_fresh, int push, int env0, int slot_base) {
+         int res_out_arg, int ecap, int scap, int rcap, int only_fresh, int push, int env0, int slot_base) {
+  /* the LoRes layouts are 96 x 96 by definition (benchmarks/__init__.py:242-274): a compile-time resolution
+   * turns every tile / group / row division and the address arithmetic into constants */
+  const int res_out = (MODE == MG_OBS_RAW) ? res_out_arg : 96;
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
   /* LoResStack and RAW keep their two views in separate planes, so the views are rendered one after the
    * other through the same shared memory (NPASS = 2, one resident view): half the footprint, twice the CTAs
@@ -746,7 +750,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
    * and the tile goes on the flat list or the busy list.  The lists reuse s_off (dead after E1). */
   uint8_t* const flat_list = reinterpret_cast<uint8_t*>(s_off);
   uint8_t* const busy_list = flat_list + RGRID * RGRID;
-  for (int tile = threadIdx.x; tile < RGRID * RGRID; tile += blockDim.x) {
+  for (int tile = threadIdx.x; tile < RGRID * RGRID; tile += RASTER_THREADS) {
     bool all_flat = true;
     int weight = 0; /* primitives a pixel of this tile may have to walk */
 #pragma unroll
@@ -905,7 +909,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
 #pragma unroll
         for (int k = 0; k < 3; k++) pre[v][k] = pre_next[v][k];
       const int cX0 = X0, cY = Y, ctile = tile;
-      const int next = item + blockDim.x;
+      const int next = item + RASTER_THREADS;
       if (next < n_items) { item_xy(next, X0, Y, tile); load_pre(X0, Y, pre_next); }
       uint32_t col[NV][4];
 #pragma unroll
