@@ -254,7 +254,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
       float hw = 0.5f * pr.radius * px_scale;
       float s0 = 0.0f;
       for (int k = 0; k < n; k++) {
-        float2 a = vs.verts[v0 + k], b = vs.verts[v0 + (k + 1) % n];
+        float2 a = vs.verts[v0 + k], b = vs.verts[v0 + (k + 1 == n ? 0 : k + 1)];
         float dx = b.x - a.x, dy = b.y - a.y;
         float L = sqrtf(fmaf(dx, dx, dy * dy));
         if (rp0 + k < vs.rcap) {
@@ -295,7 +295,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         area2 = 1.0f;
       } else {
         for (int k = 0; k < n; k++) {
-          float2 a = vs.verts[v0 + k], c = vs.verts[v0 + (k + 1) % n];
+          float2 a = vs.verts[v0 + k], c = vs.verts[v0 + (k + 1 == n ? 0 : k + 1)];
           area2 += a.x * c.y - a.y * c.x;
           l = fminf(l, a.x); r = fmaxf(r, a.x); b = fminf(b, a.y); t = fmaxf(t, a.y);
         }
@@ -359,7 +359,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
       continue;
     }
     int v0 = ra.voff[dp], n = pr.nvert, k = v - v0;
-    float2 a = vs.verts[v0 + k], b = vs.verts[v0 + (k + 1) % n];
+    float2 a = vs.verts[v0 + k], b = vs.verts[v0 + (k + 1 == n ? 0 : k + 1)];
     const RPrim& R = vs.prims[rp0];
     float sgn = R.sgn;
     float A = a.y - b.y, B = b.x - a.x;
