@@ -151,8 +151,14 @@ __device__ __forceinline__ int first_true(float est, int cmin, int cmax, F ok) {
   float e = fminf(fmaxf(est, (float)cmin - 1.0f), (float)cmax + 1.0f);
   int i = (int)ceilf(e);
   i = i < cmin ? cmin : (i > cmax + 1 ? cmax + 1 : i);
-  while (i > cmin && ok(i - 1)) i--;
-  while (i <= cmax && !ok(i)) i++;
+  /* the estimate is almost always right: the predicate fails just below i and holds at i.  Both are evaluated
+   * unconditionally so that the lanes of a warp stay converged; the search loops only run for the rare miss */
+  const bool below = ok(i - 1) && i > cmin;
+  const bool at = ok(i) || i > cmax;
+  if (below || !at) {
+    while (i > cmin && ok(i - 1)) i--;
+    while (i <= cmax && !ok(i)) i++;
+  }
   return i;
 }
 /* last index in [cmin-1, cmax] up to which the monotone predicate holds (true...true false...false) */
@@ -161,8 +167,12 @@ __device__ __forceinline__ int last_true(float est, int cmin, int cmax, F ok) {
   float e = fminf(fmaxf(est, (float)cmin - 1.0f), (float)cmax + 1.0f);
   int i = (int)floorf(e);
   i = i < cmin - 1 ? cmin - 1 : (i > cmax ? cmax : i);
-  while (i < cmax && ok(i + 1)) i++;
-  while (i >= cmin && !ok(i)) i--;
+  const bool above = ok(i + 1) && i < cmax;
+  const bool at = ok(i) || i < cmin;
+  if (above || !at) {
+    while (i < cmax && ok(i + 1)) i++;
+    while (i >= cmin && !ok(i)) i--;
+  }
   return i;
 }
 
