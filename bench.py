@@ -415,6 +415,10 @@ class Runner:
                     out['traffic_source'] = tr.get('_source')
             except Exception:  # noqa: BLE001
                 pass
+        if self.venv.device_sampling:
+            out['note'] = ('k_physics_tpe+k_finish is timed in a physics-only loop, where the reset sampler '
+                           '(k_sample_layouts, ~1 ms for the environments that finish an episode) runs serially '
+                           'after it; inside a step it runs on a side stream next to the render')
         if 'exchange' in km:
             rx = self.env.nvlink_bytes_per_step()
             carrier = 'k_stack_push' if self.env.transport == 'p2p' else 'exchange'
