@@ -226,6 +226,9 @@ int mg_create(const mg_config_t* cfg, const mg_scene_t* scenes, void* cuda_strea
   }
   if (mg_raster_smem_bytes(cfg->obs_mode, ecap, scap, rcap) > 200 * 1024)
     return fail(MG_E_INVALID, "mg_create: scene has too many draw edges for the rasteriser's shared memory%s", "");
+  if (getenv("MG_VERBOSE"))
+    fprintf(stderr, "mg_create: raster capacities: %d edges, %d span rows, %d primitives -> %zu B shared memory per CTA\n",
+            ecap, scap, rcap, mg_raster_smem_bytes(cfg->obs_mode, ecap, scap, rcap));
 
   mg_handle* h = new (std::nothrow) mg_handle();
   if (!h) return fail(MG_E_NOMEM, "mg_create: out of host memory%s", "");

@@ -78,7 +78,6 @@ struct RPrim {
   int32_t tile0;        /* offset of this primitive's (primitive, tile row) work items in the binning pass */
   float ymin, ymax;     /* vertical extent of the window-space vertices */
 };
-
 struct Camera {
   float cc, cs, cx, cy, nx, ny, S;
 };
@@ -245,6 +244,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   if (tid == 0) {
     s_misc[7] = 0; /* number of thick line segments collected by phase C */
     s_misc[8] = 0; s_misc[9] = 0; s_misc[10] = 0; s_misc[11] = 0; /* flat / heavy / light tile lists, busy-tile hand-out */
+    s_misc[3] = 0; /* primitive hand-out counter of the span phase */
   }
   /* B: window-space vertices */
   for (int v = tid; v < nv; v += nt) {
@@ -346,6 +346,9 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         if (start + nr > scap) { vs.prims[p].nrows = 0; nr = 0; } /* cannot happen with the host's bound */
         vs.prims[p].span0 = start;
         vs.prims[p].tile0 = toff + tincl - nt_rows;
+        /* the span phase works in units of 32 consecutive table rows: primitive of each unit's first row */
+        for (int u = (start + 31) >> 5; u <= (start + nr - 1) >> 5 && nr > 0; u++)
+          if (u < RLONG - RMAXLINES) s_off[u] = p;
       }
       /* thick line segments with rows: their (segment, row) items are spread over all warps in E0 */
       const unsigned lm = __ballot_sync(0xffffffffu, is_line && nr > 0);
@@ -393,65 +396,91 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     const int cnt = j1 >= j0 ? j1 - j0 + 1 : 0;
     /* edges.w = primitive | rows << 8;  eaux.w = rows that enter the item queue (long edges only: the
      * short ones -- the sides of the many-gons -- are handled one edge per lane) */
-    /* long = enters the item queue: only edges on the static candidate list can (every other edge, however
-     * many rows it bounds at an unusual resolution, takes the one-edge-per-lane path) */
-    const bool lng = cnt >= RSHORT && ra.vcand[v] != 0;
-    vs.edges[v] = make_float4(A, B, C, __int_as_float(rp0 | (cnt << 8) | (lng ? (1 << 30) : 0)));
-    vs.eaux[v] = make_float4(-B * inv, -C * inv, __int_as_float(j0), __int_as_float(lng ? cnt : 0));
+    vs.edges[v] = make_float4(A, B, C, __int_as_float(rp0 | (cnt << 8)));
+    vs.eaux[v] = make_float4(-B * inv, -C * inv, __int_as_float(j0), __int_as_float(cnt));
   }
   __syncthreads();
   RPROF(3);
-  /* E0: warp 0 turns the row counts of the edges that can be long (static candidate list) into item offsets
-   * (exclusive prefix) while the other warps initialise the span table: polygons start from their bounding
-   * columns (rows outside the vertices' y-extent are empty), thick line segments are solved directly per row */
-  const int nwarp = nt >> 5, wid = tid >> 5, lane = tid & 31;
-  if (wid == 0) {
-    int off = 0, nlong = 0;
-    const int ncand = ra.n_cand;
-    for (int base = 0; base < ncand; base += 32) {
-      const int ci = base + lane;
-      const int v = (ci < ncand) ? (int)ra.cand[ci] : nv;
-      int c = (v < nv) ? __float_as_int(vs.eaux[v].w) : 0;
-      int incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
+  /* E: SPAN TABLE.  A thread owns one (primitive, sample row) and computes the row's exact covered interval
+   * [lo, hi] on its own: it collects the edges of the primitive that can bound the row (row inside the edge's
+   * [j0, j0 + cnt), one shared-memory word per edge, no divergence) into a bit mask and then evaluates its
+   * candidates one per trip; every edge function fmaf(A, x, fmaf(B, y, C)) is monotone in x, so the covered set is
+   * [max of the lower bounds, min of the upper bounds] -- the set a brute-force per-sample test of all edges
+   * yields.  No atomics: nobody else writes the row.  Warps take primitives from a counter (painter's order:
+   * the arena, the largest, first); thick line segments are solved directly per row (row_span), their rows
+   * spread over all threads afterwards. */
+  const int lane = tid & 31;
+  {
+    /* exact bound of edge (E, X) on sample row j within the primitive's columns [c0, c1]: first (A > 0) or last
+     * (A < 0) column that holds; one search for both orientations: for A < 0 the column axis is mirrored */
+    auto edge_bound = [&](const float4& E, const float4& X, int j, int c0, int c1) {
+      const float A = E.x;
+      const float y = (float)j + 0.5f;
+      const float t = fmaf(E.y, y, E.z);
+      const int sg = (A < 0.0f) ? -1 : 1;
+      if (A != 0.0f) {
+        auto ok = [&](int u) { return fmaf(A, (float)(sg * u) + 0.5f, t) >= 0.0f; };
+        const float est = fmaf(X.x, y, X.y) - 0.5f;
+        const int u = first_true(sg > 0 ? est : -est, sg > 0 ? c0 : -c1, sg > 0 ? c1 : -c0, ok);
+        return sg * u;
       }
-      const int start = off + incl - c;
-      if (v < nv) vs.eaux[v].w = __int_as_float(start);
-      off += __shfl_sync(0xffffffffu, incl, 31);
-      /* compact list of the edges that own items: item offset << 12 | edge (MG_RV_MAX <= 4096) */
-      const unsigned has = __ballot_sync(0xffffffffu, c > 0);
-      const int k = nlong + __popc(has & ((1u << lane) - 1u));
-      if (c > 0 && k < RLONG - RMAXLINES) s_off[k] = (start << 12) | v;
-      nlong += __popc(has);
-    }
-    if (lane == 0) { s_misc[3] = off; s_misc[5] = min(nlong, RLONG - RMAXLINES); }
-  } else {
+      return (t >= 0.0f) ? c1 : c0 - 1; /* horizontal edge: the whole row holds or none of it */
+    };
     const int nlines = s_misc[7];
     const bool spread = nlines <= RMAXLINES;
-    for (int p = wid - 1; p < nrp; p += nwarp - 1) {
+    const int total_rows = s_misc[2];
+    /* work unit = 32 consecutive rows of the span table (rows are laid out primitive after primitive), handed
+     * out to warps from a counter: full lane use whatever the primitives' heights are; a unit may straddle two or
+     * three primitives */
+    for (int u = tid >> 5; u * 32 < total_rows; u += nt / 32) {
+      const int w = u * 32 + lane;
+      if (w >= total_rows) continue;
+      /* primitive of the unit's first row (table of phase D); the lane then steps forward to the primitive
+       * holding its own row (primitives without rows share offsets with their successor) */
+      int p = (u < RLONG - RMAXLINES) ? s_off[u] : 0;
+      while (p + 1 < nrp && vs.prims[p].span0 + vs.prims[p].nrows <= w) p++;
       const RPrim R = vs.prims[p];
-      if (R.ne == 0 && spread) continue;
-      for (int r = lane; r < R.nrows; r += 32) {
+      const int r = w - R.span0;
+      if (r < 0 || r >= R.nrows || (R.ne == 0 && spread)) continue;
+      const int c0 = R.col0, c1 = R.col1;
+      {
         const int j = R.row0 + r;
         short2 sp;
-        if (R.ne > 0) {
-          const float y = (float)j + 0.5f;
-          const bool outside = (y > R.ymax + 0.01f || y < R.ymin - 0.01f);
-          sp = make_short2((short)R.col0, outside ? (short)(R.col0 - 1) : (short)R.col1);
-        } else {
+        if (R.ne == 0) {
           sp = row_span(R, vs.edges, vs.eaux, j);
+        } else {
+          const float y = (float)j + 0.5f;
+          int lo = c0, hi = c1;
+          if (y > R.ymax + 0.01f || y < R.ymin - 0.01f) {
+            hi = c0 - 1; /* outside the vertices' y-extent: empty */
+          } else {
+            /* candidates in chunks of 32 edges (polygons have <= 8, the many-gons 10 / 20 / 100) */
+            for (int kb = 0; kb < (int)R.ne; kb += 32) {
+              const int kn = min(32, (int)R.ne - kb);
+              uint32_t cand = 0u;
+              for (int k = 0; k < kn; k++) {
+                const float2 jc = *reinterpret_cast<const float2*>(&vs.eaux[R.e0 + kb + k].z); /* j0, cnt */
+                cand |= ((unsigned)(j - __float_as_int(jc.x)) < (unsigned)__float_as_int(jc.y) ? 1u : 0u) << k;
+              }
+              while (cand) {
+                const int k = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                const float4 E = vs.edges[R.e0 + kb + k];
+                const int v = edge_bound(E, vs.eaux[R.e0 + kb + k], j, c0, c1);
+                if (E.x > 0.0f) lo = max(lo, v); else hi = min(hi, v);
+              }
+            }
+          }
+          sp = make_short2((short)lo, (short)hi);
         }
         vs.spans[R.span0 + r] = sp;
       }
     }
     if (spread && nlines > 0) {
-      /* (segment, row) items of the thick line segments, spread evenly over the 7 warps */
+      /* (segment, row) items of the thick line segments, spread evenly over all threads */
       int total = 0;
       for (int k = 0; k < nlines; k++) total += vs.prims[s_off[RLONG - RMAXLINES + k]].nrows;
-      for (int it = tid - 32; it < total; it += nt - 32) {
+      for (int it = tid; it < total; it += nt) {
         int k = 0, r = it;
         for (;;) {
           const int nr = vs.prims[s_off[RLONG - RMAXLINES + k]].nrows;
@@ -461,73 +490,6 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         const RPrim& R = vs.prims[s_off[RLONG - RMAXLINES + k]];
         vs.spans[R.span0 + r] = row_span(R, vs.edges, vs.eaux, R.row0 + r);
       }
-    }
-  }
-  __syncthreads();
-  RPROF(4);
-  /* E1: one work item per (polygon edge, row it can bound): the exact first / last covered column w.r.t.
-   * that edge, folded into the row's span with a compare-and-swap.  Every edge function is monotone in x,
-   * so the covered set of a row is [max of the lower bounds, min of the upper bounds] -- the same set a
-   * brute-force per-sample test of all edges yields. */
-  {
-    /* fold the bound of edge (E, X) on sample row j into that row's span */
-    auto fold = [&](const float4& E, const float4& X, int j) {
-      const RPrim& R = vs.prims[__float_as_int(E.w) & 0xFF];
-      const int c0 = R.col0, c1 = R.col1;
-      const float A = E.x;
-      const float y = (float)j + 0.5f;
-      const float t = fmaf(E.y, y, E.z);
-      uint32_t* w = reinterpret_cast<uint32_t*>(&vs.spans[R.span0 + (j - R.row0)]);
-      /* one search for both orientations: for A < 0 the column axis is mirrored (u = -i), which turns
-       * "last column that holds" into "first mirrored column that holds" */
-      const int sg = (A < 0.0f) ? -1 : 1;
-      int v;
-      if (A != 0.0f) {
-        auto ok = [&](int u) { return fmaf(A, (float)(sg * u) + 0.5f, t) >= 0.0f; };
-        const float est = fmaf(X.x, y, X.y) - 0.5f;
-        const int u = first_true(sg > 0 ? est : -est, sg > 0 ? c0 : -c1, sg > 0 ? c1 : -c0, ok);
-        v = sg * u;
-      } else {
-        v = (t >= 0.0f) ? c1 : c0 - 1; /* horizontal edge: the whole row holds or none of it */
-      }
-      /* low half = max of lower bounds, high half = min of upper bounds */
-      const int shift = (A > 0.0f) ? 0 : 16;
-      uint32_t old = *w;
-      for (;;) {
-        const int cur = (int)(short)(old >> shift);
-        if ((A > 0.0f) ? (cur >= v) : (cur <= v)) break;
-        const uint32_t prev = atomicCAS(w, old, (old & ~(0xFFFFu << shift)) | ((uint32_t)(uint16_t)v << shift));
-        if (prev == old) break;
-        old = prev;
-      }
-    };
-    /* long edges: each warp owns a contiguous chunk of (edge, row) items and its lanes take consecutive
-     * items, so neighbouring lanes work on neighbouring rows of the same edge */
-    const int n_items = s_misc[3];
-    const int chunk = ((n_items + nwarp - 1) / nwarp + 31) & ~31;
-    const int it_end = min((wid + 1) * chunk, n_items);
-    int it = wid * chunk + lane;
-    const int nlong = s_misc[5];
-    if (it < it_end) {
-      /* the long edge holding item `it`: last list entry whose offset is <= it */
-      int lo = 0, hi = nlong - 1;
-      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((s_off[mid] >> 12) <= it) lo = mid; else hi = mid - 1; }
-      int k = lo;
-      for (; it < it_end; it += 32) {
-        while (k + 1 < nlong && (s_off[k + 1] >> 12) <= it) k++;
-        const int e = s_off[k] & 4095;
-        const float4 X = vs.eaux[e];
-        fold(vs.edges[e], X, __float_as_int(X.z) + (it - __float_as_int(X.w)));
-      }
-    }
-    /* short edges: one edge per lane, a handful of rows each */
-    for (int v = tid; v < nv; v += nt) {
-      const float4 E = vs.edges[v];
-      const int cnt = (__float_as_int(E.w) >> 8) & 0x3FFF;
-      if (cnt <= 0 || ((__float_as_int(E.w) >> 30) & 1)) continue;
-      const float4 X = vs.eaux[v];
-      const int j0 = __float_as_int(X.z);
-      for (int r = 0; r < cnt; r++) fold(E, X, j0 + r);
     }
   }
   __syncthreads();
@@ -705,16 +667,17 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
    * turns every tile / group / row division and the address arithmetic into constants */
   const int res_out = (MODE == MG_OBS_RAW) ? res_out_arg : 96;
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
-  /* LoResStack and RAW keep their two views in separate planes, so the views are rendered one after the
-   * other through the same shared memory (NPASS = 2, one resident view): half the footprint, twice the CTAs
-   * per SM.  LoRes3EA interleaves both views in one pixel and keeps both resident. */
+  /* LoResStack and RAW keep their two views in separate planes: one CTA per (environment, view), so both views
+   * go through the single-view code and shared-memory footprint (blocks 2 e and 2 e + 1 serve environment e).
+   * LoRes3EA interleaves both views in one pixel and keeps both resident in one CTA. */
   constexpr bool SEQ = (MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_RAW);
   constexpr int NV = (MODE == MG_OBS_LORES3EA) ? 2 : 1;
-  constexpr int NPASS = SEQ ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_off[RLONG]; /* long-edge list; last RMAXLINES entries: thick line segments; later the tile lists */
   __shared__ int s_misc[12];
-  const int env = env0 + blockIdx.x; /* this launch covers environments [env0, env0 + gridDim.x) */
+  /* this launch covers environments [env0, env0 + gridDim.x) (SEQ: gridDim.x / 2) */
+  const int env = env0 + (SEQ ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
+  const int pass = SEQ ? (int)(blockIdx.x & 1) : 0; /* plane / view of this CTA in the two-plane layouts */
   if (env >= batch) return;
   EnvState& stg = states[env];
   const EnvState& st = stg;
@@ -744,7 +707,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
     }
   }
   const bool fresh = st.fresh != 0;
-  for (int pass = 0; pass < NPASS; pass++) {
+  {
   for (int v = 0; v < NV; v++) {
     int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
     build_view<SS>(vsm[v], st, sc, scenes[scene_index].ra, view, res_out, ecap, scap, s_off, s_misc);
@@ -977,10 +940,18 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
       store_group(X0, Y, pre, col);
     }
   }
-  if (pass + 1 < NPASS) __syncthreads(); /* the next pass rebuilds the shared tables */
   RPROF(7);
-  } /* pass */
-  if (threadIdx.x == 0 && fresh) stg.fresh = 0;
+  }
+  if (threadIdx.x == 0 && fresh) {
+    if (!SEQ) {
+      stg.fresh = 0;
+    } else {
+      /* two CTAs per environment: each leaves its mark in the flag, the second one to finish clears it (the flag
+       * stays non-zero for a sibling that starts late) */
+      const int old = atomicOr(&stg.fresh, 4 << pass);
+      if (old & (4 << (1 - pass))) stg.fresh = 0;
+    }
+  }
 }
 
 static int n_views(int mode) { /* views resident in shared memory at a time */
@@ -1015,7 +986,8 @@ static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  k_raster<MODE><<<count, RASTER_THREADS, smem, stream>>>(states, scenes, obs, newest, plane_stride, batch, res_out, ecap,
+  constexpr int ctas_per_env = (MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_RAW) ? 2 : 1;
+  k_raster<MODE><<<count * ctas_per_env, RASTER_THREADS, smem, stream>>>(states, scenes, obs, newest, plane_stride, batch, res_out, ecap,
                                                           scap, rcap, only_fresh, push, env0, slot_base);
   return cudaGetLastError();
 }
