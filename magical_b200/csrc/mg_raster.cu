@@ -34,6 +34,7 @@
  *      with three 128-bit load/store pairs, so HBM sees the algorithmic
  *      minimum: read the 3 frames that survive, write 4.
  */
+#include <cstdlib>
 #include "mg_device.cuh"
 
 #define RGRID 12           /* tiles per side */
@@ -707,6 +708,16 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
     }
   }
   const bool fresh = st.fresh != 0;
+#ifndef RASTER_NO_PREFETCH
+  /* The shading passes at the end shift this environment's frame stack (110 592 B) through registers; ask for it
+   * now, so that it travels HBM -> L2 while the span tables are built (one bulk prefetch of 4 KB per thread of the
+   * first warp; the 592 resident CTAs hold 65 MB of the 126 MB L2) */
+  if (MODE != MG_OBS_RAW && !fresh && push && threadIdx.x < 27) {
+    const size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * plane_stride : 0;
+    const uint8_t* src = obs + plane + (size_t)env * (96 * 96 * 12) + (size_t)threadIdx.x * 4096;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(4096) : "memory");
+  }
+#endif
   {
   for (int v = 0; v < NV; v++) {
     int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
@@ -984,8 +995,19 @@ static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint
   size_t smem = mg_raster_smem_bytes(MODE, ecap, scap, rcap);
   cudaError_t e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return e;
+  /* shared-memory carve-out: exactly what the resident CTAs need (registers allow 4 per SM), the rest of the 256 KB
+   * stays L1 for the scene tables every CTA of the SM reads */
+  {
+    const size_t per_cta = smem + 3200 /* static */ + 1024 /* reserved per CTA */;
+    size_t ctas = (size_t)(227 * 1024) / per_cta;
+    if (ctas > 4) ctas = 4;
+    if (ctas < 1) ctas = 1;
+    int pct = (int)((ctas * per_cta * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    if (const char* ev = getenv("MG_RASTER_CARVEOUT")) pct = atoi(ev);
+    e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e != cudaSuccess) return e;
+  }
   constexpr int ctas_per_env = (MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_RAW) ? 2 : 1;
   k_raster<MODE><<<count * ctas_per_env, RASTER_THREADS, smem, stream>>>(states, scenes, obs, newest, plane_stride, batch, res_out, ecap,
                                                           scap, rcap, only_fresh, push, env0, slot_base);

@@ -10,14 +10,14 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 lib = _native.load()
 
 
-def probe(env_id, **kw):
+def probe(env_id, stagger=1, **kw):
     venv = magical.make_vec(env_id, B, auto_reset=True, seed=1, **kw)
     venv.reset()
     g = torch.Generator(device='cuda'); g.manual_seed(0)
     ids = np.arange(B)
     for t in range(60):
         venv.step(torch.randint(0, 18, (B,), dtype=torch.int32, device='cuda', generator=g))
-        venv.reset(env_ids=ids[ids % 60 == t])
+        venv.reset(env_ids=ids[(ids // stagger) % 60 == t])
     torch.cuda.synchronize()
     acts = torch.randint(0, 18, (B,), dtype=torch.int32, device='cuda', generator=g)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -32,7 +32,9 @@ def probe(env_id, **kw):
     venv.close()
 
 
-probe('MatchRegions-Demo-LoResStack-v0')
-probe('MatchRegions-TestAll-LoResStack-v0', device_sampling=False)
-probe('MatchRegions-TestAll-LoResStack-v0', device_sampling=True)
 probe('MatchRegions-Demo-LoRes4E-v0')
+probe('MatchRegions-Demo-LoRes4E-v0', n_scenes=64)
+probe('MatchRegions-TestAll-LoRes4E-v0', n_scenes=1)
+probe('MatchRegions-TestAll-LoRes4E-v0', n_scenes=2)
+probe('MatchRegions-TestAll-LoRes4E-v0', n_scenes=8)
+probe('MatchRegions-TestAll-LoRes4E-v0', n_scenes=64)
