@@ -442,14 +442,12 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
       while (p + 1 < nrp && vs.prims[p].span0 + vs.prims[p].nrows <= w) p++;
       const RPrim R = vs.prims[p];
       const int r = w - R.span0;
-      if (r < 0 || r >= R.nrows || (R.ne == 0 && spread)) continue;
+      if (r < 0 || r >= R.nrows || R.ne == 0) continue; /* thick line segments: below */
       const int c0 = R.col0, c1 = R.col1;
       {
         const int j = R.row0 + r;
         short2 sp;
-        if (R.ne == 0) {
-          sp = row_span(R, vs.edges, vs.eaux, j);
-        } else {
+        {
           const float y = (float)j + 0.5f;
           int lo = c0, hi = c1;
           if (y > R.ymax + 0.01f || y < R.ymin - 0.01f) {
@@ -477,18 +475,22 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         vs.spans[R.span0 + r] = sp;
       }
     }
-    if (spread && nlines > 0) {
-      /* (segment, row) items of the thick line segments, spread evenly over all threads */
+    if (nlines > 0) {
+      /* (segment, row) items of the thick line segments, spread evenly over all threads.  The segments come from
+       * the list phase D made; a scene with more than RMAXLINES of them walks all primitives instead */
+      const int nl = spread ? nlines : nrp;
+      auto seg = [&](int k) { return spread ? s_off[RLONG - RMAXLINES + k] : k; };
+      auto seg_rows = [&](int k) { const RPrim& R = vs.prims[seg(k)]; return R.ne == 0 ? (int)R.nrows : 0; };
       int total = 0;
-      for (int k = 0; k < nlines; k++) total += vs.prims[s_off[RLONG - RMAXLINES + k]].nrows;
+      for (int k = 0; k < nl; k++) total += seg_rows(k);
       for (int it = tid; it < total; it += nt) {
         int k = 0, r = it;
         for (;;) {
-          const int nr = vs.prims[s_off[RLONG - RMAXLINES + k]].nrows;
+          const int nr = seg_rows(k);
           if (r < nr) break;
           r -= nr; k++;
         }
-        const RPrim& R = vs.prims[s_off[RLONG - RMAXLINES + k]];
+        const RPrim& R = vs.prims[seg(k)];
         vs.spans[R.span0 + r] = row_span(R, vs.edges, vs.eaux, R.row0 + r);
       }
     }
