@@ -161,67 +161,39 @@ __device__ __forceinline__ int first_true(float est, int cmin, int cmax, F ok) {
   }
   return i;
 }
-/* last index in [cmin-1, cmax] up to which the monotone predicate holds (true...true false...false) */
-template <class F>
-__device__ __forceinline__ int last_true(float est, int cmin, int cmax, F ok) {
-  float e = fminf(fmaxf(est, (float)cmin - 1.0f), (float)cmax + 1.0f);
-  int i = (int)floorf(e);
-  i = i < cmin - 1 ? cmin - 1 : (i > cmax ? cmax : i);
-  const bool above = ok(i + 1) && i < cmax;
-  const bool at = ok(i) || i < cmin;
-  if (above || !at) {
-    while (i < cmax && ok(i + 1)) i++;
-    while (i >= cmin && !ok(i)) i--;
-  }
-  return i;
-}
-
-/* exact covered interval of sample row j for a thick line segment R (empty => lo > hi); polygons get
- * their spans from the (edge, row) items of build_view */
-__device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restrict__ edges,
-                                          const float4* __restrict__ eaux, int j) {
-  (void)eaux;
+/* exact covered interval of sample row j for a thick line segment R (empty => lo > hi); polygons get their spans
+ * from their edges in build_view.  A sample is covered unless along < 0 || along > L || |perp| > hw: four half-lines
+ * in x, each bounded by a monotone fp32 expression, intersected in turn by the same search (columns mirrored where
+ * the predicate falls instead of rising).  One loop instead of four unrolled searches: the kernel's size matters
+ * more (instruction cache) than these few rows. */
+__device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restrict__ edges, int j) {
   int lo = R.col0, hi = R.col1;
   const float y = (float)j + 0.5f;
-  /* thick line segment: !(along < 0 || along > L || |perp| > hw), each bound monotone in x */
-  float4 p = edges[R.e0], q = edges[R.e0 + 1];
+  const float4 p = edges[R.e0], q = edges[R.e0 + 1];
   const float ry = y - p.y;
   const float ca = ry * p.w;      /* along = fmaf(rx, ux, ry*uy) */
   const float cp = -(ry * p.z);   /* perp  = fmaf(rx, uy, -(ry*ux)) */
-  const float ux = p.z, uy = p.w, L = q.x, hw = q.z;
-  auto along = [&](int i) { return fmaf(((float)i + 0.5f) - p.x, ux, ca); };
-  auto perp = [&](int i) { return fmaf(((float)i + 0.5f) - p.x, uy, cp); };
-  if (L < 0.0f) {
-    hi = lo - 1;
-  } else {
-    /* The covered set is the intersection of four half-lines (each bound is monotone in x), so the order in
-     * which they are intersected does not matter.  perp in [-hw, hw] first: for the thin borders it leaves a
-     * sample or two, and the along bounds are then usually settled by evaluating the two end columns. */
-    if (uy > 0.0f) {
-      lo = first_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
-      if (lo <= hi) hi = last_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
-    } else if (uy < 0.0f) {
-      hi = last_true(p.x + (-hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) < -hw); });
-      if (lo <= hi) lo = first_true(p.x + (hw - cp) / uy - 0.5f, lo, hi, [&](int i) { return !(perp(i) > hw); });
-    } else if (fabsf(cp) > hw) {
-      hi = lo - 1;
+  const float L = q.x, hw = q.z;
+  if (L < 0.0f) hi = lo - 1;
+#pragma unroll 1
+  for (int c = 0; c < 4 && lo <= hi; c++) {
+    /* c = 0, 1: perp >= -hw, perp <= hw (for the thin borders they leave a sample or two); 2, 3: along >= 0, <= L */
+    const bool upper = (c & 1) != 0;
+    const float coef = c < 2 ? p.w : p.z;
+    const float off = c < 2 ? cp : ca;
+    const float thr = c < 2 ? (upper ? hw : -hw) : (upper ? L : 0.0f);
+    auto holds = [&](int i) {
+      const float v = fmaf(((float)i + 0.5f) - p.x, coef, off);
+      return upper ? !(v > thr) : !(v < thr);
+    };
+    if (coef == 0.0f) {
+      if (!holds(lo)) hi = lo - 1; /* the same for every column */
+      continue;
     }
-    /* along in [0, L] */
-    if (lo <= hi) {
-      const float a0 = along(lo), a1 = along(hi);
-      const bool in0 = !(a0 < 0.0f) && !(a0 > L), in1 = !(a1 < 0.0f) && !(a1 > L);
-      if (!(in0 && in1)) { /* (monotone: both ends inside => every column between them is) */
-        if (ux > 0.0f) {
-          lo = first_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
-          if (lo <= hi) hi = last_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
-        } else if (ux < 0.0f) {
-          hi = last_true(p.x - ca / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) < 0.0f); });
-          if (lo <= hi) lo = first_true(p.x + (L - ca) / ux - 0.5f, lo, hi, [&](int i) { return !(along(i) > L); });
-        } else if (ca < 0.0f || ca > L) {
-          hi = lo - 1;
-        }
-      }
-    }
+    const int sg = ((coef > 0.0f) != upper) ? 1 : -1; /* +1: false ... true along x; -1: true ... false */
+    const float est = p.x + (thr - off) / coef - 0.5f;
+    const int u = first_true(sg > 0 ? est : -est, sg > 0 ? lo : -hi, sg > 0 ? hi : -lo, [&](int m) { return holds(sg * m); });
+    if (sg > 0) lo = u; else hi = -u;
   }
   return make_short2((short)lo, (short)hi);
 }
@@ -491,7 +463,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
           r -= nr; k++;
         }
         const RPrim& R = vs.prims[seg(k)];
-        vs.spans[R.span0 + r] = row_span(R, vs.edges, vs.eaux, R.row0 + r);
+        vs.spans[R.span0 + r] = row_span(R, vs.edges, R.row0 + r);
       }
     }
   }
