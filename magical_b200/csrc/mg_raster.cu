@@ -212,6 +212,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   /* vertex offsets, window-primitive indices and the vertex -> primitive map are static per scene (ra) */
   const int nv = min((int)ra.nv, ecap);
   const int nrp = min((int)ra.nrp, vs.rcap);
+#pragma unroll 1
   for (int i = tid; i < RGRID * RGRID * vs.rwords; i += nt) vs.tiles[i] = 0u;
   for (int i = tid; i < RGRID * RGRID; i += nt) vs.cover[i] = -1;
   if (tid == 0) {
@@ -277,6 +278,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
         l = cx - rad; r = cx + rad; b = cy - rad; t = cy + rad;
         area2 = 1.0f;
       } else {
+#pragma unroll 2
         for (int k = 0; k < n; k++) {
           float2 a = vs.verts[v0 + k], c = vs.verts[v0 + (k + 1 == n ? 0 : k + 1)];
           area2 += a.x * c.y - a.y * c.x;
@@ -454,9 +456,11 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
       auto seg = [&](int k) { return spread ? s_off[RLONG - RMAXLINES + k] : k; };
       auto seg_rows = [&](int k) { const RPrim& R = vs.prims[seg(k)]; return R.ne == 0 ? (int)R.nrows : 0; };
       int total = 0;
+#pragma unroll 1
       for (int k = 0; k < nl; k++) total += seg_rows(k);
       for (int it = tid; it < total; it += nt) {
         int k = 0, r = it;
+#pragma unroll 1
         for (;;) {
           const int nr = seg_rows(k);
           if (r < nr) break;
@@ -486,6 +490,7 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
     int umin = 32767, umax = -1;   /* hull of the covered columns */
     int cmin = -1, cmax = 32767;   /* columns covered by EVERY row of the tile row */
     bool all_rows = (a == ja && b == jb);
+#pragma unroll 2
     for (int j = a; j <= b; j++) {
       short2 s = vs.spans[R.span0 + (j - R.row0)];
       if (s.x <= s.y) {
