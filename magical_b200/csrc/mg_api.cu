@@ -112,7 +112,7 @@ static const char* scene_raster_needs(const mg_scene_t& sc, int res_full, int* e
     rprims += pr.kind == MG_PRIM_LINELOOP ? pr.nvert : 1;
     /* span-table rows: a primitive is rigid, so in any camera it spans at most its diameter */
     if (pr.kind == MG_PRIM_NGON) {
-      int r = (int)ceil(2.0 * pr.radius * S_full) + 8;
+      int r = (int)ceil(2.0 * pr.radius * S_full) + 14; /* box margins + the aligned allocation's padding */
       rows += r < res_full ? r : res_full;
     } else if ((int)pr.vert0 + pr.nvert <= MG_MAX_DVERTS) {
       const float(*dv)[2] = &sc.dverts[pr.vert0];
@@ -120,7 +120,7 @@ static const char* scene_raster_needs(const mg_scene_t& sc, int res_full, int* e
         for (int k = 0; k < pr.nvert; k++) {
           int k2 = (k + 1) % pr.nvert;
           double len = hypot((double)dv[k][0] - dv[k2][0], (double)dv[k][1] - dv[k2][1]);
-          int r = (int)ceil(len * S_full + pr.radius) + 8;
+          int r = (int)ceil(len * S_full + pr.radius) + 14;
           rows += r < res_full ? r : res_full;
         }
       } else {
@@ -130,7 +130,7 @@ static const char* scene_raster_needs(const mg_scene_t& sc, int res_full, int* e
             double d = hypot((double)dv[a][0] - dv[b][0], (double)dv[a][1] - dv[b][1]);
             if (d > diam) diam = d;
           }
-        int r = (int)ceil(diam * S_full) + 8;
+        int r = (int)ceil(diam * S_full) + 14;
         rows += r < res_full ? r : res_full;
       }
     }

@@ -310,19 +310,23 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
       const bool is_line = (p < nrp) && vs.prims[p].ne == 0 && nr > 0;
       /* tile rows the primitive's sample rows touch = its work items in the binning pass (F) */
       int nt_rows = (nr > 0) ? (min((r0 + nr - 1) / TSd, RGRID - 1) - r0 / TSd + 1) : 0;
-      int incl = nr, tincl = nt_rows;
+      /* rows are allocated in aligned groups of 4 sample rows (one output row): the allocation starts at the
+       * primitive's row0 rounded down to a multiple of 4, so that the shading pass fetches the four spans of an
+       * output row with one 16-byte load; the up to 6 padding rows hold empty spans */
+      const int alloc = nr > 0 ? (((r0 & 3) + nr + 3) & ~3) : 0;
+      int incl = alloc, tincl = nt_rows;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         int t = __shfl_up_sync(0xffffffffu, incl, d), tt = __shfl_up_sync(0xffffffffu, tincl, d);
         if (tid >= d) { incl += t; tincl += tt; }
       }
       if (p < nrp) {
-        int start = off + incl - nr;
-        if (start + nr > scap) { vs.prims[p].nrows = 0; nr = 0; } /* cannot happen with the host's bound */
-        vs.prims[p].span0 = start;
+        int start = off + incl - alloc;
+        if (start + alloc > scap) { vs.prims[p].nrows = 0; nr = 0; } /* cannot happen with the host's bound */
+        vs.prims[p].span0 = start + (nr > 0 ? (r0 & 3) : 0);
         vs.prims[p].tile0 = toff + tincl - nt_rows;
         /* the span phase works in units of 32 consecutive table rows: primitive of each unit's first row */
-        for (int u = (start + 31) >> 5; u <= (start + nr - 1) >> 5 && nr > 0; u++)
+        for (int u = (start + 31) >> 5; u <= (start + alloc - 1) >> 5 && alloc > 0; u++)
           if (u < RLONG - RMAXLINES) s_off[u] = p;
       }
       /* thick line segments with rows: their (segment, row) items are spread over all warps in E0 */
@@ -416,7 +420,11 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
       while (p + 1 < nrp && vs.prims[p].span0 + vs.prims[p].nrows <= w) p++;
       const RPrim R = vs.prims[p];
       const int r = w - R.span0;
-      if (r < 0 || r >= R.nrows || R.ne == 0) continue; /* thick line segments: below */
+      if (r < 0 || r >= R.nrows) { /* padding row of the aligned allocation: nothing covered */
+        vs.spans[w] = make_short2(1, 0);
+        continue;
+      }
+      if (R.ne == 0) continue; /* thick line segments: below */
       const int c0 = R.col0, c1 = R.col1;
       {
         const int j = R.row0 + r;
@@ -558,14 +566,29 @@ __device__ __forceinline__ void shade4(const ViewSmem& vs, int X0, int Yg, int t
         for (int i = 0; i < 4; i++) m[i] = 0u;
         uint32_t strips[SS]; /* per sample row: bit c = sample column x0 + c is covered */
 #pragma unroll
-        for (int r = 0; r < SS; r++) {
-          strips[r] = 0u;
-          int row = y0 + r - R.row0;
-          if (row >= 0 && row < R.nrows) {
-            short2 sp = vs.spans[R.span0 + row];
-            /* columns of the 4*SS-sample strip covered by this row */
-            int l = max((int)sp.x - x0, 0), h = min((int)sp.y - x0, 4 * SS - 1);
-            if (l <= h) strips[r] = (0xFFFFFFFFu >> (31 - (h - l))) << l;
+        for (int r = 0; r < SS; r++) strips[r] = 0u;
+        if (SS == 4) {
+          /* the four sample rows of this output row are one aligned group of the primitive's allocation (phase D),
+           * inside it or not at all; padding rows hold empty spans */
+          if (y0 >= (R.row0 & ~3) && y0 < (((int)R.row0 + R.nrows + 3) & ~3)) {
+            const uint4 q4 = *reinterpret_cast<const uint4*>(&vs.spans[R.span0 + (y0 - R.row0)]);
+            const uint32_t qs[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int r = 0; r < SS; r++) {
+              const int l = max((int)(short)(qs[r % 4] & 0xFFFFu) - x0, 0), h = min((int)(short)(qs[r % 4] >> 16) - x0, 4 * SS - 1);
+              if (l <= h) strips[r] = (0xFFFFFFFFu >> (31 - (h - l))) << l;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < SS; r++) {
+            int row = y0 + r - R.row0;
+            if (row >= 0 && row < R.nrows) {
+              short2 sp = vs.spans[R.span0 + row];
+              /* columns of the 4*SS-sample strip covered by this row */
+              int l = max((int)sp.x - x0, 0), h = min((int)sp.y - x0, 4 * SS - 1);
+              if (l <= h) strips[r] = (0xFFFFFFFFu >> (31 - (h - l))) << l;
+            }
           }
         }
         if (SS == 4) {
