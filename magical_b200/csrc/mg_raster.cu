@@ -200,8 +200,9 @@ __device__ __forceinline__ short2 row_span(const RPrim& R, const float4* __restr
 
 /* Build the window-space primitive set, span table and tile bins of one view. */
 template <int SS>
-__device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& sc, const mg_raster_aux_t& ra, int view,
-                           int res_out, int ecap, int scap, int* s_off /* [RLONG] */, int* s_misc) {
+__device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& sc, const mg_raster_aux_t& ra,
+                           const mg_raster_aux_t* lv_own /* device-sampled layouts: the environment's own copy */,
+                           int view, int res_out, int ecap, int scap, int* s_off /* [RLONG] */, int* s_misc) {
   RPROF_DECL
   const int tid = threadIdx.x;
   constexpr int nt = RASTER_THREADS; /* compile-time block size: no runtime divisions by the warp count */
@@ -222,8 +223,12 @@ __device__ void build_view(ViewSmem& vs, const EnvState& st, const mg_scene_t& s
   }
   /* B: window-space vertices */
   for (int v = tid; v < nv; v += nt) {
-    const float2 l = *reinterpret_cast<const float2*>(ra.lv[v]);
-    vs.verts[v] = prim_vertex(st, sc.prims[ra.vprim[v]], l.x, l.y, cam);
+    const mg_prim_t& pr = sc.prims[ra.vprim[v]];
+    /* world-fixed polygons and borders (the goal rectangles among them) come from the environment's own table
+     * when layouts are sampled on the device; everything else from the shared, cache-resident template */
+    const bool own = lv_own != nullptr && pr.kind != MG_PRIM_NGON && pr.xform != MG_XFORM_BODY;
+    const float2 l = *reinterpret_cast<const float2*>(own ? lv_own->lv[v] : ra.lv[v]);
+    vs.verts[v] = prim_vertex(st, pr, l.x, l.y, cam);
   }
   __syncthreads();
   RPROF(1);
@@ -688,8 +693,10 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
    * that just reset (their layout is still being sampled on another stream; they are drawn by a second launch) */
   if (only_fresh == 1 && st.fresh == 0) return;
   if (only_fresh == 2 && st.fresh != 0) return;
-  /* device-side layout sampling (slot_base >= 0): the sampled goal rectangles live in the environment's slot */
-  const int scene_index = slot_base >= 0 ? slot_base + env : st.scene;
+  /* device-side layout sampling (slot_base >= 0): the environment plays template st.scene; of everything the
+   * render reads only the goal rectangles' vertices were re-drawn, and those live in the environment's slot */
+  const int scene_index = st.scene;
+  const mg_raster_aux_t* lv_own = slot_base >= 0 ? &scenes[slot_base + env].ra : nullptr;
   const mg_scene_t& sc = scenes[scene_index].s;
   const float px_scale = (float)(res_out * SS) / 384.0f;
 
@@ -723,7 +730,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   {
   for (int v = 0; v < NV; v++) {
     int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
-    build_view<SS>(vsm[v], st, sc, scenes[scene_index].ra, view, res_out, ecap, scap, s_off, s_misc);
+    build_view<SS>(vsm[v], st, sc, scenes[scene_index].ra, lv_own, view, res_out, ecap, scap, s_off, s_misc);
   }
   RPROF_DECL
   const int T = res_out / RGRID;        /* output pixels per tile side (multiple of 4) */
