@@ -675,11 +675,12 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
    * turns every tile / group / row division and the address arithmetic into constants */
   const int res_out = (MODE == MG_OBS_RAW) ? res_out_arg : 96;
   constexpr int SS = (MODE == MG_OBS_RAW) ? 1 : 4;
-  /* LoResStack and RAW keep their two views in separate planes: one CTA per (environment, view), so both views
-   * go through the single-view code and shared-memory footprint (blocks 2 e and 2 e + 1 serve environment e).
-   * LoRes3EA interleaves both views in one pixel and keeps both resident in one CTA. */
-  constexpr bool SEQ = (MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_RAW);
-  constexpr int NV = (MODE == MG_OBS_LORES3EA) ? 2 : 1;
+  /* The layouts with two views (LoResStack, RAW: one plane per view; LoRes3EA: both views inside one pixel) get
+   * one CTA per (environment, view), so every view goes through the single-view code and shared-memory footprint
+   * (blocks 2 e and 2 e + 1 serve environment e; `pass` 0 = allocentric, 1 = egocentric).  In LoRes3EA the two CTAs
+   * of an environment write disjoint BYTES of the same pixels: the allo CTA bytes 0..2, the ego CTA bytes 3..11. */
+  constexpr bool SEQ = (MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_RAW || MODE == MG_OBS_LORES3EA);
+  constexpr int NV = 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_off[RLONG]; /* long-edge list; last RMAXLINES entries: thick line segments; later the tile lists */
   __shared__ int s_misc[12];
@@ -721,7 +722,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   /* The shading passes at the end shift this environment's frame stack (110 592 B) through registers; ask for it
    * now, so that it travels HBM -> L2 while the span tables are built (one bulk prefetch of 4 KB per thread of the
    * first warp; the 592 resident CTAs hold 65 MB of the 126 MB L2) */
-  if (MODE != MG_OBS_RAW && !fresh && push && threadIdx.x < 27) {
+  if (MODE != MG_OBS_RAW && !(MODE == MG_OBS_LORES3EA && pass == 0) && !fresh && push && threadIdx.x < 27) {
     const size_t plane = (MODE == MG_OBS_LORESSTACK) ? (size_t)pass * plane_stride : 0;
     const uint8_t* src = obs + plane + (size_t)env * (96 * 96 * 12) + (size_t)threadIdx.x * 4096;
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(4096) : "memory");
@@ -729,7 +730,7 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
 #endif
   {
   for (int v = 0; v < NV; v++) {
-    int view = SEQ ? pass : ((NV == 2) ? v : ((MODE == MG_OBS_LORES4A) ? 0 : 1));
+    int view = SEQ ? pass : ((MODE == MG_OBS_LORES4A) ? 0 : 1);
     build_view<SS>(vsm[v], st, sc, scenes[scene_index].ra, lv_own, view, res_out, ecap, scap, s_off, s_misc);
   }
   RPROF_DECL
@@ -780,7 +781,8 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   /* read the surviving frames of one 4-pixel group / shift, append and write it back */
   auto load_pre = [&](int X0, int Y, uint4 (&pre)[NV][3]) {
       /* issue the read of the surviving frames before shading so HBM latency overlaps the ALU work */
-      if ((MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_LORES3EA) &&
+      if ((MODE == MG_OBS_LORES4E || MODE == MG_OBS_LORES4A || MODE == MG_OBS_LORESSTACK ||
+           (MODE == MG_OBS_LORES3EA && pass == 1 && push)) &&
           !fresh) {
 #pragma unroll
         for (int v = 0; v < 1; v++) {
@@ -822,35 +824,42 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
           }
         }
       } else if (MODE == MG_OBS_LORES3EA) {
-        /* bytes 0..2 = newest allo frame; bytes 3..11 = 3 ego frames, oldest first */
-        uint4* ptr = reinterpret_cast<uint4*>(obs + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12);
-        uint32_t w[12];
-        if (!fresh) {
-          uint4 a = pre[0][0], b = pre[0][1], c = pre[0][2];
-          w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-          w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
-        }
+        /* bytes 0..2 = newest allo frame; bytes 3..11 = 3 ego frames, oldest first.  This CTA owns one of the two
+         * byte ranges of every pixel (the sibling CTA writes the other, concurrently), so it stores exactly its
+         * bytes: the allo CTA 2 + 1 bytes per pixel, the ego CTA 1 + 4 + 4 (or only the newest 1 + 2 on a redraw) */
+        uint8_t* px = obs + ((size_t)env * frame_px + (size_t)Y * res_out + X0) * 12;
+        if (pass == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          uint32_t al = col[0][i], eg = col[NV - 1][i];
-          if (fresh) {
-            w[3 * i] = al | (eg << 24);
-            w[3 * i + 1] = (eg >> 8) | (eg << 16);
-            w[3 * i + 2] = (eg >> 16) | (eg << 8);
-          } else if (!push) {
-            w[3 * i] = al | (w[3 * i] & 0xFF000000u);
-            w[3 * i + 2] = (w[3 * i + 2] & 0xFFu) | (eg << 8);
-          } else {
-            uint32_t w1 = w[3 * i + 1], w2 = w[3 * i + 2];
-            uint32_t b6 = (w1 >> 16) & 0xFF, b7 = (w1 >> 24) & 0xFF;
-            w[3 * i] = al | (b6 << 24);          /* old bytes 6..11 -> 3..8 ; new ego -> 9..11 */
-            w[3 * i + 1] = b7 | (w2 << 8);
-            w[3 * i + 2] = (w2 >> 24) | (eg << 8);
+          for (int i = 0; i < 4; i++) {
+            const uint32_t al = col[0][i];
+            *reinterpret_cast<uint16_t*>(px + 12 * i) = (uint16_t)(al & 0xFFFFu);
+            px[12 * i + 2] = (uint8_t)(al >> 16);
+          }
+        } else {
+          uint32_t w[12];
+          if (!fresh && push) {
+            uint4 a = pre[0][0], b = pre[0][1], c = pre[0][2];
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const uint32_t eg = col[0][i];
+            if (fresh) {
+              px[12 * i + 3] = (uint8_t)(eg & 0xFFu);
+              *reinterpret_cast<uint32_t*>(px + 12 * i + 4) = (eg >> 8) | (eg << 16);
+              *reinterpret_cast<uint32_t*>(px + 12 * i + 8) = (eg >> 16) | (eg << 8);
+            } else if (!push) {
+              px[12 * i + 9] = (uint8_t)(eg & 0xFFu);
+              *reinterpret_cast<uint16_t*>(px + 12 * i + 10) = (uint16_t)(eg >> 8);
+            } else {
+              const uint32_t w1 = w[3 * i + 1], w2 = w[3 * i + 2];
+              px[12 * i + 3] = (uint8_t)((w1 >> 16) & 0xFFu);  /* old bytes 6..11 -> 3..8 ; new ego -> 9..11 */
+              *reinterpret_cast<uint32_t*>(px + 12 * i + 4) = (w1 >> 24) | (w2 << 8);
+              *reinterpret_cast<uint32_t*>(px + 12 * i + 8) = (w2 >> 24) | (eg << 8);
+            }
           }
         }
-        __stcs(ptr, make_uint4(w[0], w[1], w[2], w[3]));
-        __stcs(ptr + 1, make_uint4(w[4], w[5], w[6], w[7]));
-        __stcs(ptr + 2, make_uint4(w[8], w[9], w[10], w[11]));
       } else if (MODE == MG_OBS_LORESCHW4E) {
         /* [B, 12, R, R]: plane c of frame f is channel 3f + c; 4 pixels = one u32 per plane */
         uint8_t* base = obs + (size_t)env * 12 * frame_px + (size_t)Y * res_out + X0;
@@ -974,8 +983,9 @@ k_raster(EnvState* __restrict__ states, const DeviceScene* __restrict__ scenes, 
   }
 }
 
-static int n_views(int mode) { /* views resident in shared memory at a time */
-  return (mode == MG_OBS_LORES3EA) ? 2 : 1;
+static int n_views(int mode) { /* views resident in one CTA's shared memory */
+  (void)mode;
+  return 1;
 }
 
 size_t mg_raster_smem_bytes(int mode, int ecap, int scap, int rcap) {
@@ -1017,7 +1027,7 @@ static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint
     e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e != cudaSuccess) return e;
   }
-  constexpr int ctas_per_env = (MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_RAW) ? 2 : 1;
+  constexpr int ctas_per_env = (MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_RAW || MODE == MG_OBS_LORES3EA) ? 2 : 1;
   k_raster<MODE><<<count * ctas_per_env, RASTER_THREADS, smem, stream>>>(states, scenes, obs, newest, plane_stride, batch, res_out, ecap,
                                                           scap, rcap, only_fresh, push, env0, slot_base);
   return cudaGetLastError();

@@ -36,5 +36,6 @@ probe('MatchRegions-Demo-LoRes4E-v0')
 probe('MatchRegions-TestAll-LoRes4E-v0', n_scenes=1)
 probe('MatchRegions-TestAll-LoRes4E-v0', n_scenes=64)
 probe('MatchRegions-Demo-LoResStack-v0')
+probe('MatchRegions-Demo-LoRes3EA-v0')
 probe('MatchRegions-TestAll-LoResStack-v0', device_sampling=False)
 probe('MatchRegions-TestAll-LoResStack-v0', device_sampling=True)
