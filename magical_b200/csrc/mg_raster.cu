@@ -1012,11 +1012,17 @@ static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint
                                size_t plane_stride, int batch, int res_out, int ecap, int scap, int rcap,
                                int only_fresh, int push, int env0, int count, int slot_base, cudaStream_t stream) {
   size_t smem = mg_raster_smem_bytes(MODE, ecap, scap, rcap);
-  cudaError_t e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  /* function attributes are per device and per instantiation: set them when the footprint differs from what this
+   * device's k_raster<MODE> was last configured for (handles with different scenes may alternate) */
+  static size_t configured_on[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  /* shared-memory carve-out: exactly what the resident CTAs need (registers allow 4 per SM), the rest of the 256 KB
-   * stays L1 for the scene tables every CTA of the SM reads */
-  {
+  if (configured_on[dev & 63] != smem) {
+    e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    /* shared-memory carve-out: exactly what the resident CTAs need (registers allow 4 per SM), the rest of the
+     * 256 KB stays L1 for the scene tables every CTA of the SM reads */
     const size_t per_cta = smem + 3200 /* static */ + 1024 /* reserved per CTA */;
     size_t ctas = (size_t)(227 * 1024) / per_cta;
     if (ctas > 4) ctas = 4;
@@ -1026,6 +1032,7 @@ static cudaError_t launch_mode(EnvState* states, const DeviceScene* scenes, uint
     if (const char* ev = getenv("MG_RASTER_CARVEOUT")) pct = atoi(ev);
     e = cudaFuncSetAttribute(k_raster<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e != cudaSuccess) return e;
+    configured_on[dev & 63] = smem;
   }
   constexpr int ctas_per_env = (MODE == MG_OBS_LORESSTACK || MODE == MG_OBS_RAW || MODE == MG_OBS_LORES3EA) ? 2 : 1;
   k_raster<MODE><<<count * ctas_per_env, RASTER_THREADS, smem, stream>>>(states, scenes, obs, newest, plane_stride, batch, res_out, ecap,
