@@ -13,30 +13,41 @@ import json
 import statistics
 import sys
 
-rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
-hdr = rows[0]
-ii, ki, mi, ui, vi = (hdr.index('ID'), hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Unit'),
-                      hdr.index('Metric Value'))
-scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
-per_launch = collections.defaultdict(lambda: collections.defaultdict(lambda: {'r': 0.0, 'w': 0.0}))
-for r in rows[1:]:
-    if not r[mi].startswith('dram__bytes_'):
-        continue
-    name = r[ki].split('(')[0].split('<')[0].replace('void ', '').strip()
-    per_launch[name][r[ii]]['r' if 'read' in r[mi] else 'w'] += float(r[vi].replace(',', '')) * scale[r[ui]]
-out, detail = {}, {}
-for name, launches in per_launch.items():
-    tot = sorted(v['r'] + v['w'] for v in launches.values())
-    steady = [v for v in launches.values() if v['r'] + v['w'] >= 0.5 * tot[-1]]
-    med = statistics.median(v['r'] + v['w'] for v in steady)
-    out[name] = med
-    detail[name] = {'launches': len(tot), 'full_launches': len(steady), 'median_total': med,
-                    'median_read': statistics.median(v['r'] for v in steady),
-                    'median_write': statistics.median(v['w'] for v in steady),
-                    'min_total': tot[0], 'max_total': tot[-1]}
-out['_detail'] = detail
-out['_batch'] = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
-out['_env_id'] = sys.argv[4] if len(sys.argv) > 4 else 'ClusterColour-Demo-LoRes4E-v0'
-out['_source'] = sys.argv[2] if len(sys.argv) > 2 else sys.argv[1]
-json.dump(out, open('profiles/traffic.json', 'w'), indent=1)
-print(json.dumps(out, indent=1))
+
+def compute(csv_path, batch=65536, env_id='ClusterColour-Demo-LoRes4E-v0', source=None):
+    """DRAM bytes per (steady-state) launch of every kernel in an ncu --csv metric log."""
+    rows = [r for r in csv.reader(open(csv_path)) if len(r) > 10]
+    hdr = rows[0]
+    ii, ki, mi, ui, vi = (hdr.index('ID'), hdr.index('Kernel Name'), hdr.index('Metric Name'),
+                          hdr.index('Metric Unit'), hdr.index('Metric Value'))
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+    per_launch = collections.defaultdict(lambda: collections.defaultdict(lambda: {'r': 0.0, 'w': 0.0}))
+    for r in rows[1:]:
+        if not r[mi].startswith('dram__bytes_'):
+            continue
+        name = r[ki].split('(')[0].split('<')[0].replace('void ', '').strip()
+        per_launch[name][r[ii]]['r' if 'read' in r[mi] else 'w'] += float(r[vi].replace(',', '')) * scale[r[ui]]
+    out, detail = {}, {}
+    for name, launches in per_launch.items():
+        tot = sorted(v['r'] + v['w'] for v in launches.values())
+        steady = [v for v in launches.values() if v['r'] + v['w'] >= 0.5 * tot[-1]]
+        med = statistics.median(v['r'] + v['w'] for v in steady)
+        out[name] = med
+        detail[name] = {'launches': len(tot), 'full_launches': len(steady), 'median_total': med,
+                        'median_read': statistics.median(v['r'] for v in steady),
+                        'median_write': statistics.median(v['w'] for v in steady),
+                        'min_total': tot[0], 'max_total': tot[-1]}
+    out['_detail'] = detail
+    out['_batch'] = batch
+    out['_env_id'] = env_id
+    out['_source'] = source or csv_path
+    return out
+
+
+if __name__ == '__main__':
+    # usage: make_traffic.py <ncu csv> [source note] [batch] [env id]  -> writes profiles/traffic.json
+    res = compute(sys.argv[1], int(sys.argv[3]) if len(sys.argv) > 3 else 65536,
+                  sys.argv[4] if len(sys.argv) > 4 else 'ClusterColour-Demo-LoRes4E-v0',
+                  sys.argv[2] if len(sys.argv) > 2 else None)
+    json.dump(res, open('profiles/traffic.json', 'w'), indent=1)
+    print(json.dumps(res, indent=1))
